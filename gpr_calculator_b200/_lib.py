@@ -1,0 +1,83 @@
+"""ctypes binding of libgpr_b200.so (C ABI declared in include/gpr_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpr_b200.so")
+
+c_int, c_ll, c_dbl, c_vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_void_p
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+RBF, DOT = 0, 1
+FF_FULL, FF_SYMMETRIC, FF_DIAG = 0, 1, 2
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_LINALG = 0, 1, 2, 3, 4
+
+# name -> (restype, argtypes); every symbol declared in include/gpr_b200.h
+SIGNATURES = {
+    "gprb_version": (c_int, []),
+    "gprb_last_error": (ctypes.c_char_p, []),
+    "gprb_device_info": (c_int, [c_int_p, c_int_p, c_int_p]),
+    "gprb_pack_create": (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "gprb_pack_destroy": (None, [c_vp]),
+    "gprb_pack_info": (c_int, [c_vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "gprb_pack_pair_count": (c_ll, [c_vp, c_int, c_int, c_vp]),
+    "gprb_kff": (c_int, [c_int, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_dbl, c_int, c_int, c_int,
+                         c_vp, c_ll, c_vp, c_ll, c_vp]),
+    "gprb_kef": (c_int, [c_int, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_int,
+                         c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp]),
+    "gprb_kee": (c_int, [c_int, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_int, c_vp, c_ll, c_vp, c_ll, c_vp]),
+    "gprb_kee_diag": (c_int, [c_int, c_vp, c_dbl, c_dbl, c_dbl, c_vp, c_vp]),
+    "gprb_add_noise": (c_int, [c_vp, c_ll, c_int, c_int, c_dbl, c_dbl, c_vp]),
+    "gprb_chol_factor": (c_int, [c_vp, c_ll, c_int, c_vp]),
+    "gprb_chol_solve_vec": (c_int, [c_vp, c_ll, c_int, c_vp, c_vp]),
+    "gprb_chol_inverse": (c_int, [c_vp, c_ll, c_int, c_vp, c_ll, c_vp]),
+    "gprb_lml_terms": (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "gprb_lml_grad_trace": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_ll, c_vp, c_ll, c_int, c_dbl, c_dbl, c_vp, c_vp]),
+    "gprb_w_block_sum": (c_int, [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "gprb_predict": (c_int, [c_int, c_int, c_vp, c_ll, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp]),
+}
+
+
+class GprB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libgpr_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class NotPositiveDefinite(GprB200Error):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (raises if it has not been built: no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+                "`make -C gpr_calculator_b200/csrc`. gpr_calculator_b200 has no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code):
+    if code != OK:
+        msg = load().gprb_last_error().decode("utf-8", "replace")
+        if code == ERR_LINALG:
+            raise NotPositiveDefinite(code, msg)
+        raise GprB200Error(code, msg)
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

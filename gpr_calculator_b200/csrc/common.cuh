@@ -1,0 +1,69 @@
+// Shared declarations for libgpr_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <vector>
+#include <map>
+#include "../../include/gpr_b200.h"
+
+#define GPRB_TILE_ROWS 8           // rows of one DMMA operand tile (M or N of mma.m8n8k4)
+#define GPRB_MAX_KS 8              // k-steps of 4 held in registers (d <= 32) by the MMA kernels
+#define GPRB_EPS_NORM 1e-8         // rbf_kernel.cpp:10,26
+
+void gprb_set_error(const char *fmt, ...);
+
+#define GPRB_CUDA(call)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (call);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            gprb_set_error("%s:%d CUDA error %s (%s)", __FILE__, __LINE__, cudaGetErrorName(_e), \
+                           cudaGetErrorString(_e));                                             \
+            return GPRB_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+#define GPRB_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            gprb_set_error(__VA_ARGS__);                                                        \
+            return GPRB_ERR_ARG;                                                                \
+        }                                                                                       \
+    } while (0)
+
+// Device-resident packed side of a covariance block.
+//
+// Tile layout (the unit every kernel consumes): rows are padded per group to a multiple of 8 and
+// cut into tiles of 8 rows.  One tile stores, for each component c (0 = x^, 1..3 = A~ columns),
+// the 8 x (4*ks) operand slab in k-step-major order
+//        P[((tile*ncomp + c)*ks + kstep)*32 + row*4 + kk]      (k = 4*kstep + kk, zero padded)
+// so that the m8n8k4 fragment of (c, kstep) is the 32 consecutive doubles read by lane = row*4+kk:
+// one fully coalesced 256-byte access from global memory and a conflict-free one from shared
+// memory after a verbatim bulk copy.
+struct gprb_pack {
+    int n_groups = 0, n_rows = 0, d = 0, ncols = 0, ncomp = 0, ks = 0, n_tiles = 0;
+    int device = 0;
+    std::vector<int> group_rows;   // host, [G]
+    std::vector<int> tile_ptr;     // host, [G+1]  first tile of each group
+    // per-group species histogram (non-dropped rows) for pair counting
+    std::vector<std::map<int, long long>> species;
+    bool species_ready = false;
+    // device buffers
+    double *P = nullptr;           // [n_tiles][ncomp][ks][32]
+    double *norm = nullptr;        // [n_tiles*8]  |x| of each padded row (0 for padding)
+    int *elep = nullptr;           // [n_tiles*8]  species; -1 padding; -(z+2) dropped (|x|<=eps)
+    int *tile_group = nullptr;     // [n_tiles]
+    int *d_tile_ptr = nullptr;     // [G+1]
+    int *d_group_rows = nullptr;   // [G]
+    // column-side schedule: chunks of <= CH tiles that never straddle a group
+    int n_chunks = 0;
+    int4 *chunks = nullptr;        // device [n_chunks] {tile0, ntiles, group, last_of_group}
+    std::vector<int> group_chunk_ptr;   // host [G+1]
+    int *d_group_chunk_ptr = nullptr;
+    // cached row-side schedule for the last window used (see cov_mma.cu)
+    int sched_g0 = -1, sched_g1 = -1, sched_n = 0;
+    int4 *sched = nullptr;         // device [sched_n] {tile0, ntiles, group0, flags}
+    std::vector<int4> sched_host;
+};
+
+#define GPRB_CHUNK_TILES 8         // max tiles per column chunk (8 x 8 KB = 64 KB of smem per stage)

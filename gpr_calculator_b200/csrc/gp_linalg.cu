@@ -1,0 +1,289 @@
+// gp_linalg.cu — the O(N^2) / O(N^3) GP algebra that follows the covariance build, kept on device.
+//
+// Replaces the scipy/numpy steps of GP.log_marginal_likelihood, GP.fit, GP.set_K_inv and
+// GP.predict* (gaussianprocess.py:128-202, 286-317, 338-377, 880-908).  The factorisation and
+// triangular solves are cuSOLVER (potrf / potrs / potri) and the K* K^-1 product is cuBLAS DGEMM:
+// library calls, reported separately by bench.py and not optimised (north_star).  The
+// bandwidth-bound pieces (noise, log-det, trace of (alpha alpha^T - K^-1) dK, fused mean/variance
+// row reductions) are hand-written kernels with fixed-order reductions.
+//
+// All matrices are row-major; a symmetric row-major matrix is handed to the column-major libraries
+// unchanged, "lower" here == CUBLAS_FILL_MODE_UPPER there.
+#include "common.cuh"
+#include <cusolverDn.h>
+#include <cublas_v2.h>
+
+namespace {
+
+cusolverDnHandle_t g_solver = nullptr;
+cublasHandle_t g_blas = nullptr;
+
+int handles(cudaStream_t st) {
+    if (!g_solver) {
+        if (cusolverDnCreate(&g_solver) != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnCreate failed"); return GPRB_ERR_CUDA; }
+    }
+    if (!g_blas) {
+        if (cublasCreate(&g_blas) != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasCreate failed"); return GPRB_ERR_CUDA; }
+    }
+    if (cusolverDnSetStream(g_solver, st) != CUSOLVER_STATUS_SUCCESS || cublasSetStream(g_blas, st) != CUBLAS_STATUS_SUCCESS) {
+        gprb_set_error("setting the library stream failed");
+        return GPRB_ERR_CUDA;
+    }
+    return GPRB_OK;
+}
+
+__global__ void add_noise_kernel(double *K, long long ld, int N, int NE, double ne2, double nf2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) K[(long long)i * ld + i] += (i < NE) ? ne2 : nf2;
+}
+
+// after potri on the (row-major) lower triangle: copy it to the upper triangle
+__global__ void mirror_lower_kernel(double *A, long long ld, int N) {
+    __shared__ double t[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const int i = bi * 32 + threadIdx.y, j = bj * 32 + threadIdx.x;
+    if (i < N && j < N) t[threadIdx.y][threadIdx.x] = A[(long long)i * ld + j];
+    __syncthreads();
+    const int ti = bj * 32 + threadIdx.y, tj = bi * 32 + threadIdx.x;   // transposed block
+    if (ti < N && tj < N && tj > ti) A[(long long)ti * ld + tj] = t[threadIdx.x][threadIdx.y];
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) for (int i = 0; i < nw; i++) r += sh[i];
+    return r;   // valid in thread 0
+}
+
+__global__ void lml_terms_kernel(const double *L, long long ld, int N, const double *y, const double *alpha, double *out) {
+    __shared__ double sh[32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        a += log(L[(long long)i * ld + i]);
+        b += y[i] * alpha[i];
+    }
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+
+// partial[block] = sum over the block's rows of sum_j (alpha_i alpha_j - Kinv_ij) * dK_ij
+// partial2[block] = sum over rows of (alpha_i^2 - Kinv_ii) * w_i
+__global__ void __launch_bounds__(256) trace_kernel(int N, int r0, int r1, const double *__restrict__ alpha,
+                                                    const double *__restrict__ Kinv, long long ldi,
+                                                    const double *__restrict__ dK, long long lddk,
+                                                    int NE, double we, double wf, double *partial) {
+    __shared__ double sh[32];
+    double acc = 0.0, acc2 = 0.0;
+    for (int i = r0 + blockIdx.x; i < r1; i += gridDim.x) {
+        const double ai = alpha[i];
+        const double *ki = Kinv + (long long)i * ldi;
+        if (dK) {
+            const double *di = dK + (long long)(i - r0) * lddk;
+            for (int j = threadIdx.x; j < N; j += blockDim.x) acc = fma(fma(ai, alpha[j], -ki[j]), di[j], acc);
+        }
+        if (threadIdx.x == 0) acc2 += (ai * ai - ki[i]) * (i < NE ? we : wf);
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = acc; partial[2 * blockIdx.x + 1] = acc2; }
+}
+
+__global__ void block_sum_kernel(int N, int r0, int r1, int c0, int c1, const double *__restrict__ alpha,
+                                 const double *__restrict__ Kinv, long long ldi, double *partial) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = r0 + blockIdx.x; i < r1; i += gridDim.x) {
+        const double ai = alpha[i];
+        const double *ki = Kinv + (long long)i * ldi;
+        for (int j = c0 + threadIdx.x; j < c1; j += blockDim.x) acc += fma(ai, alpha[j], -ki[j]);
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = acc; partial[2 * blockIdx.x + 1] = 0.0; }
+}
+
+__global__ void final_sum_kernel(const double *partial, int n, double *out) {
+    // one thread, fixed order: deterministic
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < n; i++) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+        out[0] = 0.5 * a; out[1] = 0.5 * b;
+    }
+}
+
+// one CTA per test row: mean = Ks[i,:].alpha ; var = max(diag - Ks[i,:].W[i,:], 0)
+__global__ void __launch_bounds__(256) predict_rows_kernel(int N, const double *__restrict__ Ks, long long ldks,
+                                                           const double *__restrict__ alpha, const double *__restrict__ W,
+                                                           const double *__restrict__ diag, double *mean, double *var) {
+    __shared__ double sh[32];
+    const int i = blockIdx.x;
+    const double *k = Ks + (long long)i * ldks;
+    double m = 0.0, v = 0.0;
+    if (W) {
+        const double *w = W + (long long)i * N;
+        for (int j = threadIdx.x; j < N; j += blockDim.x) { const double kj = k[j]; m = fma(kj, alpha[j], m); v = fma(kj, w[j], v); }
+    } else {
+        for (int j = threadIdx.x; j < N; j += blockDim.x) m = fma(k[j], alpha[j], m);
+    }
+    m = block_sum(m, sh);
+    v = block_sum(v, sh);
+    if (threadIdx.x == 0) {
+        mean[i] = m;
+        if (var) { const double r = diag[i] - v; var[i] = r < 0.0 ? 0.0 : r; }   // gaussianprocess.py:906-907
+    }
+}
+
+int copy_scalars(double *host, const double *dev, int n, cudaStream_t st) {
+    GPRB_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GPRB_CUDA(cudaStreamSynchronize(st));
+    return GPRB_OK;
+}
+
+}  // namespace
+
+extern "C" int gprb_add_noise(double *K, long long ldk, int N, int NE, double noise_e, double noise_f, void *stream) {
+    GPRB_REQUIRE(K && N >= 0, "gprb_add_noise: bad argument");
+    if (N == 0) return GPRB_OK;
+    add_noise_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(K, ldk, N, NE, noise_e * noise_e, noise_f * noise_f);
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+extern "C" int gprb_chol_factor(double *K, long long ldk, int N, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(K && N > 0, "gprb_chol_factor: bad argument");
+    int rc = handles(st);
+    if (rc) return rc;
+    int lwork = 0;
+    if (cusolverDnDpotrf_bufferSize(g_solver, CUBLAS_FILL_MODE_UPPER, N, K, (int)ldk, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+        gprb_set_error("potrf_bufferSize failed"); return GPRB_ERR_CUDA;
+    }
+    double *work = nullptr; int *info = nullptr;
+    GPRB_CUDA(cudaMallocAsync((void **)&work, (size_t)(lwork > 0 ? lwork : 1) * sizeof(double), st));
+    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
+    cusolverStatus_t cs = cusolverDnDpotrf(g_solver, CUBLAS_FILL_MODE_UPPER, N, K, (int)ldk, work, lwork, info);
+    int hinfo = -1;
+    GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GPRB_CUDA(cudaFreeAsync(work, st));
+    GPRB_CUDA(cudaFreeAsync(info, st));
+    GPRB_CUDA(cudaStreamSynchronize(st));
+    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotrf status %d", (int)cs); return GPRB_ERR_CUDA; }
+    if (hinfo != 0) { gprb_set_error("matrix not positive definite (potrf info = %d)", hinfo); return GPRB_ERR_LINALG; }
+    return GPRB_OK;
+}
+
+extern "C" int gprb_chol_solve_vec(const double *L, long long ldl, int N, double *b, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(L && b && N > 0, "gprb_chol_solve_vec: bad argument");
+    int rc = handles(st);
+    if (rc) return rc;
+    int *info = nullptr;
+    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
+    cusolverStatus_t cs = cusolverDnDpotrs(g_solver, CUBLAS_FILL_MODE_UPPER, N, 1, L, (int)ldl, b, N, info);
+    GPRB_CUDA(cudaFreeAsync(info, st));
+    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotrs status %d", (int)cs); return GPRB_ERR_CUDA; }
+    return GPRB_OK;
+}
+
+extern "C" int gprb_chol_inverse(const double *L, long long ldl, int N, double *Kinv, long long ldi, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(L && Kinv && N > 0, "gprb_chol_inverse: bad argument");
+    int rc = handles(st);
+    if (rc) return rc;
+    GPRB_CUDA(cudaMemcpy2DAsync(Kinv, ldi * sizeof(double), L, ldl * sizeof(double), (size_t)N * sizeof(double), N,
+                                cudaMemcpyDeviceToDevice, st));
+    int lwork = 0;
+    if (cusolverDnDpotri_bufferSize(g_solver, CUBLAS_FILL_MODE_UPPER, N, Kinv, (int)ldi, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+        gprb_set_error("potri_bufferSize failed"); return GPRB_ERR_CUDA;
+    }
+    double *work = nullptr; int *info = nullptr;
+    GPRB_CUDA(cudaMallocAsync((void **)&work, (size_t)(lwork > 0 ? lwork : 1) * sizeof(double), st));
+    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
+    cusolverStatus_t cs = cusolverDnDpotri(g_solver, CUBLAS_FILL_MODE_UPPER, N, Kinv, (int)ldi, work, lwork, info);
+    GPRB_CUDA(cudaFreeAsync(work, st));
+    GPRB_CUDA(cudaFreeAsync(info, st));
+    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotri status %d", (int)cs); return GPRB_ERR_CUDA; }
+    dim3 grid((N + 31) / 32, (N + 31) / 32), block(32, 32);
+    mirror_lower_kernel<<<grid, block, 0, st>>>(Kinv, ldi, N);
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+extern "C" int gprb_lml_terms(const double *L, long long ldl, int N, const double *y, const double *alpha,
+                              double *out_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(L && y && alpha && out_host && N > 0, "gprb_lml_terms: bad argument");
+    double *d = nullptr;
+    GPRB_CUDA(cudaMallocAsync((void **)&d, 2 * sizeof(double), st));
+    lml_terms_kernel<<<1, 1024, 0, st>>>(L, ldl, N, y, alpha, d);
+    GPRB_CUDA(cudaGetLastError());
+    int rc = copy_scalars(out_host, d, 2, st);
+    cudaFreeAsync(d, st);
+    return rc;
+}
+
+extern "C" int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha, const double *Kinv, long long ldi,
+                                   const double *dK_rows, long long lddk, int NE, double we, double wf,
+                                   double *out_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(alpha && Kinv && out_host && 0 <= r0 && r0 <= r1 && r1 <= N, "gprb_lml_grad_trace: bad argument");
+    out_host[0] = out_host[1] = 0.0;
+    if (r0 == r1) return GPRB_OK;
+    const int blocks = (r1 - r0) < 1184 ? (r1 - r0) : 1184;   // 8 x 148
+    double *d = nullptr;
+    GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
+    trace_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, alpha, Kinv, ldi, dK_rows, lddk, NE, we, wf, d);
+    GPRB_CUDA(cudaGetLastError());
+    final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, d + 2 * blocks);
+    GPRB_CUDA(cudaGetLastError());
+    int rc = copy_scalars(out_host, d + 2 * blocks, 2, st);
+    cudaFreeAsync(d, st);
+    return rc;
+}
+
+extern "C" int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const double *alpha, const double *Kinv,
+                                long long ldi, double *out_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(alpha && Kinv && out_host && 0 <= r0 && r0 <= r1 && r1 <= N && 0 <= c0 && c0 <= c1 && c1 <= N,
+                 "gprb_w_block_sum: bad argument");
+    out_host[0] = 0.0;
+    if (r0 == r1 || c0 == c1) return GPRB_OK;
+    const int blocks = (r1 - r0) < 1184 ? (r1 - r0) : 1184;
+    double *d = nullptr;
+    GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
+    block_sum_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, c0, c1, alpha, Kinv, ldi, d);
+    GPRB_CUDA(cudaGetLastError());
+    final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, d + 2 * blocks);
+    GPRB_CUDA(cudaGetLastError());
+    double tmp[2];
+    int rc = copy_scalars(tmp, d + 2 * blocks, 2, st);
+    out_host[0] = tmp[0];
+    cudaFreeAsync(d, st);
+    return rc;
+}
+
+extern "C" int gprb_predict(int m, int N, const double *Ks, long long ldks, const double *alpha,
+                            const double *Kinv, long long ldi, const double *diag,
+                            double *mean, double *var, double *work, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(Ks && alpha && mean && m >= 0 && N > 0, "gprb_predict: bad argument");
+    if (m == 0) return GPRB_OK;
+    if (var) {
+        GPRB_REQUIRE(Kinv && diag && work, "gprb_predict: variance needs Kinv, diag and work");
+        int rc = handles(st);
+        if (rc) return rc;
+        // row-major work[m,N] = Ks[m,N] . Kinv[N,N]  ==  column-major work^T = Kinv^T . Ks^T
+        const double one = 1.0, zero = 0.0;
+        cublasStatus_t bs = cublasDgemm(g_blas, CUBLAS_OP_N, CUBLAS_OP_N, N, m, N, &one, Kinv, (int)ldi, Ks, (int)ldks,
+                                        &zero, work, N);
+        if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDgemm status %d", (int)bs); return GPRB_ERR_CUDA; }
+    }
+    predict_rows_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, var ? work : nullptr, diag, mean, var);
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}

@@ -1,0 +1,239 @@
+// pack.cu — device-resident packed operands (`gprb_pack`) and the row-preparation kernel.
+//
+// Replaces, for the whole life of a training set, what the reference redoes on every kernel call:
+// list_to_tuple (utilities.py:340-390), the ravel().tolist() marshalling (rbf_kernel.py:40-45,
+// 246-252) and the per-pair norm / projection arithmetic (rbf_kernel.cpp:364-399).
+#include "common.cuh"
+#include <cstring>
+#include <string>
+
+static thread_local std::string g_err;
+
+void gprb_set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+extern "C" const char *gprb_last_error(void) { return g_err.c_str(); }
+extern "C" int gprb_version(void) { return 100; }
+
+extern "C" int gprb_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+    int dev = 0;
+    GPRB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    GPRB_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return GPRB_OK;
+}
+
+// One warp per padded row.  HBM-bound: reads 8*d*(1+ncols) bytes and writes 8*4ks*(1+ncols) per row.
+__global__ void prep_rows_kernel(int n_padded, int d, int ncols, int ks,
+                                 const double *__restrict__ x, const double *__restrict__ dxdr,
+                                 const int *__restrict__ ele, const int *__restrict__ src_row,
+                                 double *__restrict__ P, double *__restrict__ norm_out,
+                                 int *__restrict__ elep) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= n_padded) return;
+    const int ncomp = 1 + ncols;
+    const int tile = warp >> 3, r = warp & 7;
+    const int kp = 4 * ks;
+    const int src = src_row[warp];
+    double *Pt = P + (size_t)tile * ncomp * ks * 32;
+    if (src < 0) {   // padding row
+        for (int c = 0; c < ncomp; c++)
+            for (int k = lane; k < kp; k += 32) Pt[((size_t)c * ks + (k >> 2)) * 32 + r * 4 + (k & 3)] = 0.0;
+        if (lane == 0) { norm_out[warp] = 0.0; elep[warp] = -1; }
+        return;
+    }
+    const double *xr = x + (size_t)src * d;
+    double ss = 0.0;
+    for (int k = lane; k < d; k += 32) { double v = xr[k]; ss += v * v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const double n = sqrt(ss);
+    const bool dropped = !(n > GPRB_EPS_NORM);
+    const double inv = dropped ? 0.0 : 1.0 / n;
+    // t_c = x^ . A[:,c]
+    double t[9];
+    const double *Ar = ncols ? dxdr + (size_t)src * d * ncols : nullptr;
+    for (int c = 0; c < ncols; c++) {
+        double acc = 0.0;
+        for (int k = lane; k < d; k += 32) acc += (xr[k] * inv) * Ar[(size_t)k * ncols + c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        t[c] = acc;
+    }
+    for (int k = lane; k < kp; k += 32) {
+        const size_t off = (size_t)(k >> 2) * 32 + r * 4 + (k & 3);
+        const double xh = (k < d) ? xr[k] * inv : 0.0;
+        Pt[off] = xh;
+        for (int c = 0; c < ncols; c++) {
+            double v = 0.0;
+            if (k < d && !dropped) v = (Ar[(size_t)k * ncols + c] - xh * t[c]) * inv;
+            Pt[(size_t)(c + 1) * ks * 32 + off] = v;
+        }
+    }
+    if (lane == 0) {
+        norm_out[warp] = n;
+        const int z = ele[src];
+        elep[warp] = dropped ? -(z + 2) : z;
+    }
+}
+
+static bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+static int stage_input(const T *any, size_t count, const T **dev, T **owned, cudaStream_t st) {
+    *owned = nullptr;
+    if (count == 0 || any == nullptr) { *dev = nullptr; return GPRB_OK; }
+    if (is_device_ptr(any)) { *dev = any; return GPRB_OK; }
+    GPRB_CUDA(cudaMallocAsync((void **)owned, count * sizeof(T), st));
+    GPRB_CUDA(cudaMemcpyAsync(*owned, any, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    *dev = *owned;
+    return GPRB_OK;
+}
+
+extern "C" void gprb_pack_destroy(gprb_pack *p) {
+    if (!p) return;
+    cudaFree(p->P); cudaFree(p->norm); cudaFree(p->elep); cudaFree(p->tile_group);
+    cudaFree(p->d_tile_ptr); cudaFree(p->d_group_rows); cudaFree(p->chunks);
+    cudaFree(p->d_group_chunk_ptr); cudaFree(p->sched);
+    delete p;
+}
+
+extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_rows_host, int d, int ncols,
+                                const double *x_any, const double *dxdr_any, const int *ele_any, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(out != nullptr, "gprb_pack_create: out is NULL");
+    *out = nullptr;
+    GPRB_REQUIRE(n_groups >= 0 && d > 0, "gprb_pack_create: bad sizes n_groups=%d d=%d", n_groups, d);
+    GPRB_REQUIRE(ncols == 0 || ncols == 3, "gprb_pack_create: ncols must be 0 (energy) or 3 (force), got %d", ncols);
+    GPRB_REQUIRE(ncols == 0 || dxdr_any != nullptr || n_groups == 0, "gprb_pack_create: dxdr is NULL for a force pack");
+    gprb_pack *p = new gprb_pack();
+    GPRB_CUDA(cudaGetDevice(&p->device));
+    p->n_groups = n_groups; p->d = d; p->ncols = ncols; p->ncomp = 1 + ncols; p->ks = (d + 3) / 4;
+    p->group_rows.assign(group_rows_host, group_rows_host + n_groups);
+    p->tile_ptr.resize(n_groups + 1);
+    p->group_chunk_ptr.resize(n_groups + 1);
+    long long rows = 0;
+    int tiles = 0;
+    std::vector<int4> chunks;
+    for (int g = 0; g < n_groups; g++) {
+        int ng = p->group_rows[g];
+        if (ng < 0) { delete p; GPRB_REQUIRE(false, "gprb_pack_create: negative group size"); }
+        p->tile_ptr[g] = tiles;
+        p->group_chunk_ptr[g] = (int)chunks.size();
+        int nt = ng > 0 ? (ng + GPRB_TILE_ROWS - 1) / GPRB_TILE_ROWS : 1;   // empty groups keep one padding tile
+        for (int t0 = 0; t0 < nt; t0 += GPRB_CHUNK_TILES) {
+            int n = nt - t0 < GPRB_CHUNK_TILES ? nt - t0 : GPRB_CHUNK_TILES;
+            chunks.push_back(make_int4(tiles + t0, n, g, t0 + n == nt ? 1 : 0));
+        }
+        tiles += nt;
+        rows += ng;
+    }
+    p->tile_ptr[n_groups] = tiles;
+    p->group_chunk_ptr[n_groups] = (int)chunks.size();
+    p->n_tiles = tiles; p->n_rows = (int)rows; p->n_chunks = (int)chunks.size();
+    if (rows > 0 && (x_any == nullptr || ele_any == nullptr)) { delete p; GPRB_REQUIRE(false, "gprb_pack_create: x/ele NULL"); }
+
+    const int n_padded = tiles * GPRB_TILE_ROWS;
+    std::vector<int> src(n_padded, -1), tgroup(tiles, 0);
+    {
+        int r = 0;
+        for (int g = 0; g < n_groups; g++) {
+            for (int t = p->tile_ptr[g]; t < p->tile_ptr[g + 1]; t++) tgroup[t] = g;
+            for (int i = 0; i < p->group_rows[g]; i++) src[p->tile_ptr[g] * GPRB_TILE_ROWS + i] = r++;
+        }
+    }
+    if (tiles == 0) { *out = p; return GPRB_OK; }
+
+    int *d_src = nullptr;
+    const size_t pbytes = (size_t)tiles * p->ncomp * p->ks * 32 * sizeof(double);
+#define PK_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { gprb_set_error("%s:%d CUDA error %s", __FILE__, __LINE__, cudaGetErrorString(_e)); gprb_pack_destroy(p); return GPRB_ERR_CUDA; } } while (0)
+    PK_CUDA(cudaMalloc((void **)&p->P, pbytes));
+    PK_CUDA(cudaMalloc((void **)&p->norm, (size_t)n_padded * sizeof(double)));
+    PK_CUDA(cudaMalloc((void **)&p->elep, (size_t)n_padded * sizeof(int)));
+    PK_CUDA(cudaMalloc((void **)&p->tile_group, (size_t)tiles * sizeof(int)));
+    PK_CUDA(cudaMalloc((void **)&p->d_tile_ptr, (size_t)(n_groups + 1) * sizeof(int)));
+    PK_CUDA(cudaMalloc((void **)&p->d_group_rows, (size_t)(n_groups > 0 ? n_groups : 1) * sizeof(int)));
+    PK_CUDA(cudaMalloc((void **)&p->chunks, chunks.size() * sizeof(int4)));
+    PK_CUDA(cudaMalloc((void **)&p->d_group_chunk_ptr, (size_t)(n_groups + 1) * sizeof(int)));
+    PK_CUDA(cudaMallocAsync((void **)&d_src, (size_t)n_padded * sizeof(int), st));
+    PK_CUDA(cudaMemcpyAsync(d_src, src.data(), (size_t)n_padded * sizeof(int), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(p->tile_group, tgroup.data(), (size_t)tiles * sizeof(int), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(p->d_tile_ptr, p->tile_ptr.data(), (size_t)(n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (n_groups > 0)
+        PK_CUDA(cudaMemcpyAsync(p->d_group_rows, p->group_rows.data(), (size_t)n_groups * sizeof(int), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(p->chunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(p->d_group_chunk_ptr, p->group_chunk_ptr.data(), (size_t)(n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+
+    const double *dx = nullptr, *ddx = nullptr; const int *de = nullptr;
+    double *ox = nullptr, *odx = nullptr; int *oe = nullptr;
+    int rc;
+    if ((rc = stage_input(x_any, (size_t)rows * d, &dx, &ox, st)) ||
+        (rc = stage_input(dxdr_any, ncols ? (size_t)rows * d * ncols : 0, &ddx, &odx, st)) ||
+        (rc = stage_input(ele_any, (size_t)rows, &de, &oe, st))) { gprb_pack_destroy(p); return rc; }
+    {
+        const int threads = 256, wpb = threads / 32;
+        const int blocks = (n_padded + wpb - 1) / wpb;
+        prep_rows_kernel<<<blocks, threads, 0, st>>>(n_padded, d, ncols, p->ks, dx, ddx, de, d_src,
+                                                     p->P, p->norm, p->elep);
+        PK_CUDA(cudaGetLastError());
+    }
+    if (ox) PK_CUDA(cudaFreeAsync(ox, st));
+    if (odx) PK_CUDA(cudaFreeAsync(odx, st));
+    if (oe) PK_CUDA(cudaFreeAsync(oe, st));
+    PK_CUDA(cudaFreeAsync(d_src, st));
+    // the host vectors (src, tgroup, chunks) die at return: pageable H2D copies have been staged by then,
+    // but make that explicit and surface asynchronous faults of the prep kernel here.
+    PK_CUDA(cudaStreamSynchronize(st));
+#undef PK_CUDA
+    *out = p;
+    return GPRB_OK;
+}
+
+extern "C" int gprb_pack_info(const gprb_pack *p, int *n_groups, int *n_rows, int *d, int *ncols, int *n_tiles) {
+    GPRB_REQUIRE(p != nullptr, "gprb_pack_info: NULL pack");
+    if (n_groups) *n_groups = p->n_groups;
+    if (n_rows) *n_rows = p->n_rows;
+    if (d) *d = p->d;
+    if (ncols) *ncols = p->ncols;
+    if (n_tiles) *n_tiles = p->n_tiles;
+    return GPRB_OK;
+}
+
+static int ensure_species(gprb_pack *p) {
+    if (p->species_ready) return GPRB_OK;
+    std::vector<int> e((size_t)p->n_tiles * GPRB_TILE_ROWS);
+    if (!e.empty()) GPRB_CUDA(cudaMemcpy(e.data(), p->elep, e.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    p->species.assign(p->n_groups, {});
+    for (int g = 0; g < p->n_groups; g++)
+        for (int r = p->tile_ptr[g] * GPRB_TILE_ROWS; r < p->tile_ptr[g + 1] * GPRB_TILE_ROWS; r++)
+            if (e[r] >= 0) p->species[g][e[r]]++;
+    p->species_ready = true;
+    return GPRB_OK;
+}
+
+extern "C" long long gprb_pack_pair_count(const gprb_pack *a_, int g0, int g1, const gprb_pack *b_) {
+    gprb_pack *a = const_cast<gprb_pack *>(a_), *b = const_cast<gprb_pack *>(b_);
+    if (!a || !b || ensure_species(a) || ensure_species(b)) return -1;
+    std::map<int, long long> tot;
+    for (auto &m : b->species) for (auto &kv : m) tot[kv.first] += kv.second;
+    long long pairs = 0;
+    if (g0 < 0) g0 = 0;
+    if (g1 > a->n_groups) g1 = a->n_groups;
+    for (int g = g0; g < g1; g++)
+        for (auto &kv : a->species[g]) { auto it = tot.find(kv.first); if (it != tot.end()) pairs += kv.second * it->second; }
+    return pairs;
+}

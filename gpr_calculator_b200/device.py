@@ -1,0 +1,262 @@
+"""Device-side plumbing: packs (device-resident operands) and covariance assembly.
+
+PyTorch is used only as the owner of device buffers and streams; every computation is a call
+into libgpr_b200.so (include/gpr_b200.h).  There is no CPU fallback.
+"""
+import ctypes
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import c_vp, c_int
+
+F64 = torch.float64
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("gpr_calculator_b200 needs an NVIDIA B200 (CUDA device); there is no CPU fallback")
+    _lib.load()
+
+
+def stream():
+    return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or NULL)."""
+    return c_vp(0) if t is None else c_vp(t.data_ptr())
+
+
+def empty(*shape):
+    return torch.empty(shape, dtype=F64, device="cuda")
+
+
+class Pack:
+    """Device-resident packed side of a covariance block (``gprb_pack``).
+
+    x [R, d] float64, ele [R] int, indices = rows per group (the reference's packed tuple layout,
+    utilities.py:340-390); dxdr [R, d, 3] makes it a force pack.  Arrays may be numpy (host) or
+    torch CUDA tensors.
+    """
+
+    def __init__(self, x, ele, indices, dxdr=None):
+        require_cuda()
+        self.handle = c_vp(0)
+        keep = []
+
+        def as_ptr(a, dtype_np, dtype_t):
+            if a is None:
+                return c_vp(0)
+            if isinstance(a, torch.Tensor):
+                a = a.to(dtype=dtype_t).contiguous()
+                keep.append(a)
+                return c_vp(a.data_ptr())
+            a = np.ascontiguousarray(a, dtype=dtype_np)
+            keep.append(a)
+            return c_vp(a.ctypes.data)
+
+        rows = np.ascontiguousarray(np.asarray(indices, dtype=np.int64), dtype=np.int32)
+        n_rows = int(rows.sum()) if len(rows) else 0
+        if x is None or len(x) == 0:
+            d = 1 if x is None or getattr(x, "ndim", 2) < 2 else int(x.shape[1])
+        else:
+            d = int(x.shape[1])
+            if int(x.shape[0]) != n_rows:
+                raise ValueError("sum(indices)=%d does not match the %d rows of x" % (n_rows, int(x.shape[0])))
+            if int(len(ele)) != n_rows:
+                raise ValueError("ele has %d entries for %d rows" % (len(ele), n_rows))
+            if dxdr is not None and tuple(dxdr.shape) != (n_rows, d, 3):
+                raise ValueError("dxdr must have shape (%d, %d, 3), got %s" % (n_rows, d, tuple(dxdr.shape)))
+        self.ncols = 0 if dxdr is None else 3
+        self.n_groups = len(rows)
+        self.n_rows = n_rows
+        self.d = d
+        self.indices = [int(v) for v in rows]
+        _lib.call("gprb_pack_create", ctypes.byref(self.handle), c_int(len(rows)),
+                  c_vp(rows.ctypes.data) if len(rows) else c_vp(0), c_int(d), c_int(self.ncols),
+                  as_ptr(x, np.float64, F64), as_ptr(dxdr, np.float64, F64), as_ptr(ele, np.int32, torch.int32), stream())
+
+    def pair_count(self, other, g0=0, g1=None):
+        g1 = self.n_groups if g1 is None else g1
+        return int(_lib.load().gprb_pack_pair_count(self.handle, g0, g1, other.handle))
+
+    @property
+    def n_out(self):
+        """Rows this side contributes to a covariance matrix."""
+        return self.n_groups * (3 if self.ncols else 1)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().gprb_pack_destroy(self.handle)
+                self.handle = c_vp(0)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# conversion of the reference's data containers into packs, with a cache for the training set
+# ------------------------------------------------------------------------------------------------
+_CACHE = {}
+
+
+def _root(a):
+    while isinstance(getattr(a, "base", None), np.ndarray):
+        a = a.base
+    return a
+
+
+def _cached(key_arr, n_groups, build):
+    if not isinstance(key_arr, np.ndarray) or key_arr.size == 0:
+        return build()
+    key = (key_arr.__array_interface__["data"][0], key_arr.shape, n_groups)
+    hit = _CACHE.get(key)
+    if hit is not None and hit[0]() is not None:
+        return hit[1]
+    root = _root(key_arr)
+    pack = build()
+    for k in [k for k, v in _CACHE.items() if v[0]() is None]:
+        del _CACHE[k]
+    try:
+        _CACHE[key] = (weakref.ref(root), pack)
+    except TypeError:
+        pass
+    return pack
+
+
+def clear_cache():
+    _CACHE.clear()
+
+
+def energy_pack(data):
+    """`data`: packed tuple (X, ELE, indices) or list of (x, ele) (kee_C input, rbf_kernel.py:26-30)."""
+    if data is None:
+        return None
+    if isinstance(data, Pack):
+        return data
+    if isinstance(data, tuple):
+        X, ELE, indices = data
+        if len(indices) == 0:
+            return None
+        return _cached(X, len(indices), lambda: Pack(X, ELE, indices))
+    if len(data) == 0:
+        return None
+    from .utilities import list_to_tuple
+    X, ELE, indices = list_to_tuple(list(data), mode="energy")
+    return Pack(X, ELE, indices)
+
+
+def force_pack(data):
+    """`data`: packed tuple (X, dXdR, ELE, indices), or list / object ndarray of (x, dxdr, ele)."""
+    if data is None:
+        return None
+    if isinstance(data, Pack):
+        return data
+    if isinstance(data, tuple):
+        X, dXdR, ELE, indices = data
+        if len(indices) == 0:
+            return None
+        return _cached(X, len(indices), lambda: Pack(X, ELE, indices, dxdr=dXdR[:, :, :3] if dXdR.shape[2] != 3 else dXdR))
+    if len(data) == 0:
+        return None
+    from .utilities import list_to_tuple
+    X, dXdR, ELE, indices = list_to_tuple(list(data), stress=False)
+    return Pack(X, ELE, indices, dxdr=dXdR)
+
+
+def packs_of(data):
+    """dict {'energy':…, 'force':…} -> (energy Pack or None, force Pack or None)."""
+    e = energy_pack(data["energy"]) if "energy" in data else None
+    f = force_pack(data["force"]) if "force" in data else None
+    return e, f
+
+
+# ------------------------------------------------------------------------------------------------
+# covariance assembly  [[K_ee, K_ef], [K_fe, K_ff]]  (kernels/base.py:3-30 build_covariance)
+# ------------------------------------------------------------------------------------------------
+def k_total_device(kernel, p0, p1, zeta, side1, side2=None, use_tol=True, tol=1e-10, grad=False,
+                   zeta_ef=None, zeta_ff=None, window=None, symmetric=True):
+    """Build the covariance between two (energy Pack, force Pack) sides on the current CUDA device.
+
+    window = ((e0, e1), (f0, f1)): only the rows of side-1 energy groups [e0,e1) and force groups
+    [f0,f1) are computed (row-block sharding).  Returns (K, dK) torch tensors of shape
+    [rows, NE2 + 3 NF2]; dK is dK/dl for RBF when grad=True, else None.
+    """
+    require_cuda()
+    e1, f1 = side1
+    same = side2 is None
+    e2, f2 = side1 if same else side2
+    zeta_ef = zeta if zeta_ef is None else zeta_ef
+    zeta_ff = zeta if zeta_ff is None else zeta_ff
+    NE1 = e1.n_groups if e1 is not None else 0
+    NF1 = f1.n_groups if f1 is not None else 0
+    NE2 = e2.n_groups if e2 is not None else 0
+    NF2 = f2.n_groups if f2 is not None else 0
+    if window is None:
+        (ea, eb), (fa, fb) = (0, NE1), (0, NF1)
+    else:
+        (ea, eb), (fa, fb) = window
+    full = (ea, eb, fa, fb) == (0, NE1, 0, NF1)
+    n_rows = (eb - ea) + 3 * (fb - fa)
+    n_cols = NE2 + 3 * NF2
+    # zero-filled so that blocks without both sides (or empty windows) are defined
+    K = torch.zeros((n_rows, n_cols), dtype=F64, device="cuda")
+    dK = torch.zeros((n_rows, n_cols), dtype=F64, device="cuda") if grad else None
+    if n_rows == 0 or n_cols == 0:
+        return K, dK
+    ld = n_cols
+    st = stream()
+    esz = K.element_size()
+
+    def at(t, r, c):
+        return c_vp(0) if t is None else c_vp(t.data_ptr() + (r * ld + c) * esz)
+
+    r_f = eb - ea          # first force row of the block
+    if e1 is not None and e2 is not None and eb > ea:
+        _lib.call("gprb_kee", kernel, e1.handle, e2.handle, p0, p1, float(zeta), ea, eb,
+                  at(K, 0, 0), ld, at(dK, 0, 0), ld, st)
+    if same and full and e1 is not None and f1 is not None:
+        # one pass writes K_ef and its transpose K_fe
+        _lib.call("gprb_kef", kernel, e1.handle, f1.handle, p0, p1, float(zeta_ef), 0, NF1,
+                  at(K, 0, NE2), ld, at(K, r_f, 0), ld, at(dK, 0, NE2), ld, at(dK, r_f, 0), ld, st)
+    else:
+        if e1 is not None and f2 is not None and eb > ea:
+            # rows = my energy groups, all force columns: compute the full-height block and keep my rows
+            if (ea, eb) == (0, NE1):
+                _lib.call("gprb_kef", kernel, e1.handle, f2.handle, p0, p1, float(zeta_ef), 0, NF2,
+                          at(K, 0, NE2), ld, c_vp(0), 0, at(dK, 0, NE2), ld, c_vp(0), 0, st)
+            else:
+                tmp = torch.zeros((NE1, 3 * NF2), dtype=F64, device="cuda")
+                dtmp = torch.zeros((NE1, 3 * NF2), dtype=F64, device="cuda") if grad else None
+                _lib.call("gprb_kef", kernel, e1.handle, f2.handle, p0, p1, float(zeta_ef), 0, NF2,
+                          ptr(tmp), 3 * NF2, c_vp(0), 0, ptr(dtmp), 3 * NF2, c_vp(0), 0, st)
+                K[:eb - ea, NE2:] = tmp[ea:eb]
+                if grad:
+                    dK[:eb - ea, NE2:] = dtmp[ea:eb]
+        if f1 is not None and e2 is not None and fb > fa:
+            _lib.call("gprb_kef", kernel, e2.handle, f1.handle, p0, p1, float(zeta_ef), fa, fb,
+                      c_vp(0), 0, at(K, r_f, 0), ld, c_vp(0), 0, at(dK, r_f, 0), ld, st)
+    if f1 is not None and f2 is not None and fb > fa:
+        mode = _lib.FF_SYMMETRIC if (same and full and symmetric) else _lib.FF_FULL
+        _lib.call("gprb_kff", kernel, f1.handle, f2.handle, p0, p1, float(zeta_ff), int(bool(use_tol)), float(tol),
+                  mode, fa, fb, at(K, r_f, NE2), ld, at(dK, r_f, NE2), ld, st)
+    return K, dK
+
+
+def diag_device(kernel, p0, p1, zeta, side, tol=1e-12):
+    """Prior variance of every row of `side` (RBF_mb.diag, RBF_mb.py:62-133; Dot_mb.diag)."""
+    require_cuda()
+    e, f = side
+    NE = e.n_groups if e is not None else 0
+    NF = f.n_groups if f is not None else 0
+    out = torch.zeros(NE + 3 * NF, dtype=F64, device="cuda")
+    st = stream()
+    if e is not None:
+        _lib.call("gprb_kee_diag", kernel, e.handle, p0, p1, float(zeta), ptr(out), st)
+    if f is not None:
+        _lib.call("gprb_kff", kernel, f.handle, f.handle, p0, p1, float(zeta), 1, float(tol), _lib.FF_DIAG, 0, NF,
+                  c_vp(out.data_ptr() + NE * 8), 0, c_vp(0), 0, st)
+    return out

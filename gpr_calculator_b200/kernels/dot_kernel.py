@@ -1,0 +1,54 @@
+"""Function-level Dot covariance blocks on the B200 (mirror of gpr_calc/kernels/dot_kernel.py)."""
+import numpy as np
+
+from .. import _lib
+from ..device import energy_pack, force_pack, empty, ptr, stream, require_cuda, c_vp
+
+
+def _host(t):
+    return t.cpu().numpy()
+
+
+def kee_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False):
+    """dot_kernel.py:9-63.  d/dsigma0 is the reference's constant 0.8*2*sigma^2*sigma0 (:58)."""
+    require_cuda()
+    e1, e2 = energy_pack(X1), energy_pack(X2)
+    K = empty(e1.n_groups, e2.n_groups)
+    _lib.call("gprb_kee", _lib.DOT, e1.handle, e2.handle, float(sigma), float(sigma0), float(zeta), 0, e1.n_groups,
+              ptr(K), e2.n_groups, c_vp(0), 0, stream())
+    C = _host(K)
+    if grad:
+        return C, 2 * C / sigma, 0.8 * 2 * sigma ** 2 * sigma0 * np.ones(C.shape)
+    return C
+
+
+def kef_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False, transpose=False):
+    """dot_kernel.py:66-160 (sigma0 does not enter; d/dsigma0 = 0, :154)."""
+    require_cuda()
+    if stress:
+        raise NotImplementedError("stress blocks are not part of the B200 hot path yet (SURVEY.md §8f)")
+    e, f = energy_pack(X1), force_pack(X2)
+    K = empty(e.n_groups, 3 * f.n_groups)
+    _lib.call("gprb_kef", _lib.DOT, e.handle, f.handle, float(sigma), float(sigma0), float(zeta), 0, f.n_groups,
+              ptr(K), 3 * f.n_groups, c_vp(0), 0, c_vp(0), 0, c_vp(0), 0, stream())
+    C = _host(K)
+    if transpose:
+        C = C.T
+    if grad:
+        return C, 2 * C / sigma, np.zeros(C.shape)
+    return C
+
+
+def kff_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False):
+    """dot_kernel.py:162-270 (no pair cut; d/dsigma0 = 0, :265)."""
+    require_cuda()
+    if stress:
+        raise NotImplementedError("stress blocks are not part of the B200 hot path yet (SURVEY.md §8f)")
+    f1, f2 = force_pack(X1), force_pack(X2)
+    K = empty(3 * f1.n_groups, 3 * f2.n_groups)
+    _lib.call("gprb_kff", _lib.DOT, f1.handle, f2.handle, float(sigma), float(sigma0), float(zeta), 0, 0.0,
+              _lib.FF_FULL, 0, f1.n_groups, ptr(K), 3 * f2.n_groups, c_vp(0), 0, stream())
+    C = _host(K)
+    if grad:
+        return C, 2 * C / sigma, np.zeros(C.shape)
+    return C

@@ -1,0 +1,133 @@
+/*
+ * gpr_b200.h — C ABI of libgpr_b200.so, the B200 (sm_100a) implementation of the covariance hot
+ * path of MaterSim/GPR_calculator.
+ *
+ * This header is the drop-in boundary.  The reference binds 13 scalar CPU loops through cffi
+ * (gpr_calc/kernels/rbf_kernel.h:4-38, dot_kernel.h:4-27, loaded by rbf_kernel.py:4 and
+ * dot_kernel.py:4).  Each entry point below names the reference symbol(s) it replaces.
+ *
+ * Differences from the reference ABI, all deliberate:
+ *   - inputs are packed ONCE into a device-resident `gprb_pack` (pre-normalised rows in the DMMA
+ *     tile layout) instead of being re-marshalled for every call (rbf_kernel.py:40-45);
+ *   - groups are described by a host array of rows-per-group (the reference's `indices` list),
+ *     not by per-row group ids;
+ *   - outputs are OVERWRITTEN (the reference accumulates into caller-zeroed buffers), already
+ *     carry the wrapper normalisations (1/n_I, 1/(n_I n_J), sigma^2 zeta ...) and can be written
+ *     straight into a sub-block of a larger row-major matrix through a leading dimension;
+ *   - every call takes a cudaStream_t (as void*) and returns an int status
+ *     (0 = ok; see gprb_last_error()); nothing falls back to the CPU;
+ *   - a group window [grp_begin, grp_end) on side 1 selects the row block a rank owns
+ *     (replaces the mpi4py row split of RBF_mb.py:471-481).
+ *
+ * Pointer conventions: `*_host` = host memory, `*_dev` = device memory, `*_any` = either (UVA).
+ * All matrices are row-major float64.  Threading: calls on different streams may be issued
+ * from different host threads; a pack must not be destroyed while a call using it is in flight.
+ */
+#ifndef GPR_B200_H
+#define GPR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gprb_pack gprb_pack;
+
+enum { GPRB_OK = 0, GPRB_ERR_ARG = 1, GPRB_ERR_CUDA = 2, GPRB_ERR_UNSUPPORTED = 3, GPRB_ERR_LINALG = 4 };
+enum { GPRB_KERNEL_RBF = 0, GPRB_KERNEL_DOT = 1 };
+/* mode of the force-force builder */
+enum { GPRB_FF_FULL = 0,      /* every (I,J) block of the window                                  */
+       GPRB_FF_SYMMETRIC = 1, /* side1 is side2: evaluate J >= I only and mirror the block         */
+       GPRB_FF_DIAG = 2 };    /* only the diagonal entries of the (I,I) blocks -> vector [3*G]     */
+
+int gprb_version(void);
+const char *gprb_last_error(void);   /* thread-local message of the last failing call */
+int gprb_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- packing -------------------------------------------------------------------------------
+ * Replaces utilities.list_to_tuple (utilities.py:340-390) + the per-call cffi marshalling and the
+ * per-pair norm recomputation (rbf_kernel.cpp:364-381).
+ *   ncols = 0 : energy rows (x only)          -> tiles of [x^]
+ *   ncols = 3 : force rows (x, dxdr[.,d,3])   -> tiles of [x^; A~_x; A~_y; A~_z]
+ * with x^ = x/|x| and A~ = (I - x^ x^T) dxdr / |x|.  Rows with |x| <= 1e-8 are dropped as in
+ * rbf_kernel.cpp:26,37.  group_rows_host[g] = number of rows of group g (the `indices` list).
+ * x_any/dxdr_any/ele_any may be host or device pointers. */
+int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_rows_host, int d, int ncols,
+                     const double *x_any, const double *dxdr_any, const int *ele_any, void *stream);
+void gprb_pack_destroy(gprb_pack *p);
+int gprb_pack_info(const gprb_pack *p, int *n_groups, int *n_rows, int *d, int *ncols, int *n_tiles);
+/* number of same-species, non-dropped row pairs between groups [g0,g1) of a and all groups of b
+ * (the unit of work of SURVEY.md §8d); computed on the host from cached per-group species counts */
+long long gprb_pack_pair_count(const gprb_pack *a, int g0, int g1, const gprb_pack *b);
+
+/* ---- covariance blocks ------------------------------------------------------------------------
+ * kernel = GPRB_KERNEL_RBF: p0 = sigma, p1 = l.   GPRB_KERNEL_DOT: p0 = sigma, p1 = sigma0.
+ * dK_dev may be NULL (no hyper-parameter gradient).  For RBF dK is dK/dl; dK/dsigma = 2K/sigma is
+ * never materialised.  For DOT the gradient blocks are closed-form constants and are not produced.
+ *
+ * gprb_kff : force-force block.  Replaces rbf_kff_many (rbf_kernel.cpp:341-473, use_tol=1),
+ *            rbf_kff_many_with_grad (:475-640, use_tol=0, dK_dev != NULL), dot_kff_many
+ *            (dot_kernel.cpp:217-336) and their wrappers kff_C (rbf_kernel.py:191-337,
+ *            dot_kernel.py:162-270).
+ *            K[(3(I-grp_begin)+c)*ldk + 3J+e]; in GPRB_FF_SYMMETRIC mode side 1 must be side 2,
+ *            the window must be the whole set and the mirrored entries are written too;
+ *            in GPRB_FF_DIAG mode K is a vector [3*(grp_end-grp_begin)]. */
+int gprb_kff(int kernel, const gprb_pack *f1, const gprb_pack *f2, double p0, double p1, double zeta,
+             int use_tol, double tol, int mode, int grp_begin, int grp_end,
+             double *K_dev, long long ldk, double *dK_dev, long long lddk, void *stream);
+
+/* gprb_kef : energy-force block K_ef[I, 3J+c] (I = energy group of `e`, J = force group of `f`),
+ *            window over the FORCE groups.  Replaces rbf_kef_many / _with_grad
+ *            (rbf_kernel.cpp:101-253), dot_kef_many (dot_kernel.cpp:58-130), kef_C.
+ *            Kef_dev[I*ld_ef + 3(J-grp_begin)+c] and/or its transpose
+ *            Kfe_dev[(3(J-grp_begin)+c)*ld_fe + I]; either may be NULL. */
+int gprb_kef(int kernel, const gprb_pack *e, const gprb_pack *f, double p0, double p1, double zeta,
+             int grp_begin, int grp_end,
+             double *Kef_dev, long long ld_ef, double *Kfe_dev, long long ld_fe,
+             double *dKef_dev, long long ld_def, double *dKfe_dev, long long ld_dfe, void *stream);
+
+/* gprb_kee : energy-energy block K[(I-grp_begin)*ldk + J].  Replaces rbf_kee_many / _with_grad
+ *            (rbf_kernel.cpp:5-98), dot_kee_many (dot_kernel.cpp:5-56), kee_C. */
+int gprb_kee(int kernel, const gprb_pack *e1, const gprb_pack *e2, double p0, double p1, double zeta,
+             int grp_begin, int grp_end, double *K_dev, long long ldk, double *dK_dev, long long lddk,
+             void *stream);
+
+/* gprb_kee_diag : prior variance of energy rows with the eps-regularised numpy formula the
+ *            reference uses only in diag() (kernels/base.py:107-130 K_ee_RBF, Dot_mb.py:177-202). */
+int gprb_kee_diag(int kernel, const gprb_pack *e, double p0, double p1, double zeta,
+                  double *out_dev, void *stream);
+
+/* ---- GP algebra on device (gaussianprocess.py:128-202, 286-317, 319-379, 880-908) ------------ */
+/* K[i,i] += (i < NE ? noise_e^2 : noise_f^2)                       (gaussianprocess.py:165-173) */
+int gprb_add_noise(double *K_dev, long long ldk, int N, int NE, double noise_e, double noise_f, void *stream);
+/* In-place Cholesky K = L L^T (cuSOLVER potrf).  Returns GPRB_ERR_LINALG if not positive definite
+ * (the reference maps that to LML = -inf, gaussianprocess.py:174-177). */
+int gprb_chol_factor(double *K_dev, long long ldk, int N, void *stream);
+/* Solve (L L^T) X = B in place for nrhs right-hand sides stored as columns of a row-major
+ * [N, nrhs] matrix when nrhs == 1, i.e. a plain vector (cuSOLVER potrs). */
+int gprb_chol_solve_vec(const double *L_dev, long long ldl, int N, double *b_dev, void *stream);
+/* Kinv = (L L^T)^-1, full symmetric matrix, out of place (cuSOLVER potri + mirror)
+ * (gaussianprocess.py:128-131, 195). */
+int gprb_chol_inverse(const double *L_dev, long long ldl, int N, double *Kinv_dev, long long ldi, void *stream);
+/* out_host[0] = sum_i log L_ii ; out_host[1] = y.alpha                 (gaussianprocess.py:183-186) */
+int gprb_lml_terms(const double *L_dev, long long ldl, int N, const double *y_dev, const double *alpha_dev,
+                   double *out_host, void *stream);
+/* out_host[0] = 1/2 sum_{i in [r0,r1), j} (alpha_i alpha_j - Kinv_ij) dK_ij  with dK given for
+ * rows [r0,r1) only (row-block sharded; all-reduce the scalar across ranks).
+ * out_host[1] = 1/2 sum_i (alpha_i^2 - Kinv_ii) * w_i, w_i = (i<NE ? we : wf) over the same rows
+ * (noise / sigma terms).                                           (gaussianprocess.py:188-198) */
+int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha_dev, const double *Kinv_dev, long long ldi,
+                        const double *dK_rows_dev, long long lddk, int NE, double we, double wf,
+                        double *out_host, void *stream);
+/* 1/2 sum over the block [r0,r1) x [c0,c1) of (alpha_i alpha_j - Kinv_ij)   (Dot d/dsigma0 term) */
+int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const double *alpha_dev, const double *Kinv_dev,
+                     long long ldi, double *out_host, void *stream);
+/* mean[i] = Ks[i,:].alpha ;  if var_dev: var[i] = max(diag[i] - Ks[i,:] Kinv Ks[i,:]^T, 0)
+ * (cuBLAS DGEMM + fused row reduction; gaussianprocess.py:880, 904-908).  work_dev: [m, N] scratch. */
+int gprb_predict(int m, int N, const double *Ks_dev, long long ldks, const double *alpha_dev,
+                 const double *Kinv_dev, long long ldi, const double *diag_dev,
+                 double *mean_dev, double *var_dev, double *work_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPR_B200_H */
