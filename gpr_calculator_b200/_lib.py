@@ -38,6 +38,10 @@ SIGNATURES = {
     "gprb_lml_grad_trace": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_ll, c_vp, c_ll, c_int, c_dbl, c_dbl, c_vp, c_vp]),
     "gprb_w_block_sum": (c_int, [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "gprb_predict": (c_int, [c_int, c_int, c_vp, c_ll, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gprb_so3_neighbors": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gprb_so3_radial": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp]),
+    "gprb_so3_power": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_dbl, c_dbl, c_vp,
+                               c_int, c_vp, c_vp, c_vp, c_vp]),
 }
 
 

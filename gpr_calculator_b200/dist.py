@@ -1,0 +1,89 @@
+"""Row-block sharding of the covariance matrix over GPUs (one process per GPU, NCCL via torch.distributed).
+
+Replaces the reference's mpi4py pattern — every rank computes a row slab, rank 0 gathers pickles,
+vstacks and broadcasts (RBF_mb.py:471-521, gaussianprocess.py:246-247,305-306) — with:
+  * contiguous row blocks of training groups balanced by cost (rows of the group),
+  * one in-place all-gather of the slabs into the full K on every GPU,
+  * dK/dtheta never gathered: each rank traces its own rows, scalars are all-reduced.
+With the gloo backend (CPU tensors) the same partition / gather logic is exercised in the tests.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def split_groups(costs, parts):
+    """Contiguous partition of len(costs) groups into `parts` blocks with balanced total cost.
+
+    Returns `parts + 1` boundaries b with b[0] = 0 and b[-1] = len(costs)."""
+    costs = np.asarray(costs, dtype=np.float64)
+    n = len(costs)
+    if n == 0:
+        return [0] * (parts + 1)
+    cum = np.concatenate(([0.0], np.cumsum(costs)))
+    total = cum[-1]
+    bounds = [0]
+    for p in range(1, parts):
+        target = total * p / parts
+        j = int(np.searchsorted(cum, target, side="left"))
+        if j > 0 and abs(cum[j - 1] - target) <= abs(cum[min(j, n)] - target):
+            j -= 1
+        j = min(max(j, bounds[-1]), n)
+        bounds.append(j)
+    bounds.append(n)
+    return bounds
+
+
+def row_windows(e_rows, f_rows, parts):
+    """Per-rank windows ((e0,e1),(f0,f1)) over energy groups and force groups.
+
+    Energy and force groups are partitioned independently so that every rank gets an equal share
+    of both block rows (the force block dominates: cost ~ rows of the centre)."""
+    eb = split_groups(e_rows, parts)
+    fb = split_groups(f_rows, parts)
+    return [((eb[r], eb[r + 1]), (fb[r], fb[r + 1])) for r in range(parts)]
+
+
+def window_row_ranges(windows, NE):
+    """Row ranges in the assembled matrix covered by each window: list of [(lo,hi) energy, (lo,hi) force]."""
+    return [((e0, e1), (NE + 3 * f0, NE + 3 * f1)) for (e0, e1), (f0, f1) in windows]
+
+
+def gather_rows(K_local, windows, NE, N, group=None):
+    """All-gather row slabs into the full [N, N_cols] matrix on every rank.
+
+    K_local holds this rank's rows: first its energy rows, then its force rows."""
+    rank, size = world()
+    n_cols = K_local.shape[1]
+    if size == 1:
+        return K_local
+    counts = [(e1 - e0) + 3 * (f1 - f0) for (e0, e1), (f0, f1) in windows]
+    mx = max(counts)
+    # equal-sized exchange buffers (all_gather_into_tensor needs them); padding rows are dropped below
+    send = torch.zeros((mx, n_cols), dtype=K_local.dtype, device=K_local.device)
+    send[:counts[rank]] = K_local
+    recv = torch.empty((size * mx, n_cols), dtype=K_local.dtype, device=K_local.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    K = torch.empty((N, n_cols), dtype=K_local.dtype, device=K_local.device)
+    for r, ((e0, e1), (f0, f1)) in enumerate(windows):
+        blk = recv[r * mx:r * mx + counts[r]]
+        ne = e1 - e0
+        K[e0:e1] = blk[:ne]
+        K[NE + 3 * f0:NE + 3 * f1] = blk[ne:]
+    return K
+
+
+def all_reduce_sum(values, device="cpu", group=None):
+    """Sum a small list of python floats over ranks."""
+    rank, size = world()
+    if size == 1:
+        return list(values)
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return [float(v) for v in t.cpu()]

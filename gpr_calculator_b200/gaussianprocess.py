@@ -1,0 +1,846 @@
+"""Gaussian-process regressor with the covariance hot path on the B200.
+
+Drop-in for ``gpr_calc.gaussianprocess.GP`` (gaussianprocess.py:22-1161): same constructor, public
+methods, training-set containers, printed ``Loss:`` lines and guard behaviour.  What changed is
+where the arithmetic runs:
+
+* ``log_marginal_likelihood`` / ``fit`` (gaussianprocess.py:133-202, 222-317): K and dK/dl are
+  built on device by the kernel object, the noise is added, Cholesky / alpha / K^-1 come from
+  cuSOLVER (potrf / potrs / potri) and the gradient is the trace kernel of libgpr_b200 — K never
+  visits the host.  L-BFGS-B stays scipy on the host, as in the reference (:215-219).
+* ``predict`` / ``predict_structure`` (:319-379, 834-918): K* on device, mean and variance with
+  the explicit K^-1 the reference uses (:128-131, 904-908), negative variances clipped to 0.
+* multi-GPU: with torch.distributed initialised (one process per GPU), each rank builds a row
+  block of K / dK, K is all-gathered, the gradient trace is all-reduced (dist.py).  This replaces
+  the mpi4py gather/bcast and the redundant allreduce of :246-247.
+
+Persistence to an ASE database (:632-821) needs ASE and is outside the hot path;
+the json part of save/load is kept.
+"""
+import json
+import logging
+import os
+from copy import deepcopy
+
+import numpy as np
+import torch
+from scipy.optimize import minimize
+
+from . import _lib
+from . import dist as gdist
+from .device import F64, c_vp, packs_of, ptr, require_cuda, stream
+from .kernels.Dot_mb import Dot_mb
+from .kernels.RBF_mb import RBF_mb
+from .utilities import (atomic_numbers, convert_train_data, force_rows, list_to_tuple, metric_values, new_pt,
+                        tuple_to_list)
+
+
+def _lazy_SO3():
+    from .SO3 import SO3
+    return SO3
+
+
+class GP():
+    """
+    Gaussian Process Regressor class to fit the interatomic potential from reference energy/forces.
+
+    Main APIs: fit(), predict_structure(struc), add_structure((struc, energy, forces)), sparsify()
+
+    Args:
+        kernel (callable): compute the covariance matrix
+        descriptor (callable): compute the structure to descriptor
+        base_potential (callable): compute the base potential before GPR
+        f_coef (float): the coefficient of force noise relative to energy
+        noise_e (float or list): energy noise, or [init, lower, upper] to optimise it
+    """
+
+    def __init__(self, kernel, descriptor,
+                 base_potential=None,
+                 noise_e=0.005,
+                 noise_f=0.1,
+                 f_coef=10,
+                 log_file="gpr.log"):
+
+        self.log_file = log_file
+        self.logging = logging.getLogger("gpr_calculator_b200.%x" % id(self))
+        self.logging.setLevel(logging.INFO)
+        self.logging.propagate = False
+        if log_file is not None and not self.logging.handlers:
+            try:
+                h = logging.FileHandler(log_file)
+                h.setFormatter(logging.Formatter('%(asctime)s| %(message)s'))
+                self.logging.addHandler(h)
+            except OSError:
+                self.logging.addHandler(logging.NullHandler())
+
+        self.rank, self.size = gdist.world()
+        if type(noise_e) is not list:
+            self.noise_e = noise_e
+            self.noise_f = noise_f
+            self.noise_bounds = None
+        else:
+            self.noise_e = noise_e[0]
+            self.noise_f = noise_f[0]
+            self.noise_bounds = noise_e[1:]
+        self.f_coef = f_coef
+        self.error = None
+
+        self.descriptor = descriptor
+        self.kernel = kernel
+        self.base_potential = base_potential
+
+        self.x = None
+        self.train_x = None
+        self.train_y = None
+        self.train_db = None
+        self._alpha_dev = None
+        self._L_dev = None
+        self._Kinv_dev = None
+        self.N_energy = 0
+        self.N_forces = 0
+        self.N_energy_queue = 0
+        self.N_forces_queue = 0
+        self.N_queue = 0
+
+        self.fits = 0
+        self.use_base = 0
+        self.use_surrogate = 0
+        # device timers of the last fit (ms): covariance builds vs library factorisations
+        self.timings = {}
+
+        if self.rank == 0:
+            self.logging.info(self)
+
+    # -- numpy views of the device-resident factors (reference attributes L_, alpha_, _K_inv) ----
+    @property
+    def alpha_(self):
+        return None if self._alpha_dev is None else self._alpha_dev.cpu().numpy().reshape(-1, 1)
+
+    @alpha_.setter
+    def alpha_(self, v):
+        self._alpha_dev = None if v is None else torch.as_tensor(np.asarray(v, dtype=np.float64).ravel(), device="cuda")
+
+    @property
+    def L_(self):
+        if self._L_dev is None:
+            return None
+        return np.tril(self._L_dev.cpu().numpy())
+
+    @L_.setter
+    def L_(self, v):
+        self._L_dev = None if v is None else torch.as_tensor(np.asarray(v, dtype=np.float64), device="cuda").contiguous()
+
+    @property
+    def _K_inv(self):
+        return None if self._Kinv_dev is None else self._Kinv_dev.cpu().numpy()
+
+    @_K_inv.setter
+    def _K_inv(self, v):
+        self._Kinv_dev = None if v is None else torch.as_tensor(np.asarray(v, dtype=np.float64), device="cuda").contiguous()
+
+    def __str__(self):
+        s = f"------Gaussian Process Regression ({self.rank}/{self.size})------\n"
+        s += "Kernel: {:s}".format(str(self.kernel))
+        if hasattr(self, "train_x"):
+            s += " {:d} energy ({:.5f})".format(self.N_energy, self.noise_e)
+            s += " {:d} forces ({:.5f})\n".format(self.N_forces, self.noise_f)
+        if self.use_base > 0:
+            N1, N2, N3 = self.use_base, self.use_surrogate, self.fits
+            s += "Total base/surrogate/gpr_fit calls: {}/{}/{}\n".format(N1, N2, N3)
+        return s
+
+    def todict(self):
+        return {}
+
+    def __repr__(self):
+        return str(self)
+
+    # ---------------------------------------------------------------------------------------------
+    # device algebra
+    # ---------------------------------------------------------------------------------------------
+    def _n_energy_rows(self, train_x=None):
+        train_x = self.train_x if train_x is None else train_x
+        e = train_x.get('energy', [])
+        if isinstance(e, tuple):
+            return len(e[-1])
+        return len(e)
+
+    def _build_K(self, grad, f_tol=1e-10):
+        """Training covariance (and dK/dl) on this device; row-block sharded when distributed."""
+        rank, size = gdist.world()
+        if size == 1:
+            return self.kernel.k_total_device(self.train_x, None, f_tol=f_tol, grad=grad) + (None,)
+        e, f = packs_of(self.train_x)
+        NE = e.n_groups if e is not None else 0
+        windows = gdist.row_windows(e.indices if e is not None else [], f.indices if f is not None else [], size)
+        K_loc, dK_loc = self.kernel.k_total_device(self.train_x, None, f_tol=f_tol, grad=grad, window=windows[rank])
+        N = NE + 3 * (f.n_groups if f is not None else 0)
+        K = gdist.gather_rows(K_loc, windows, NE, N)
+        return K, dK_loc, (windows, NE)
+
+    def _factor(self, K, noise_e, noise_f):
+        """K += noise; in-place Cholesky; alpha = K^-1 y.  Returns alpha (device vector)."""
+        N = K.shape[0]
+        NE = self._n_energy_rows()
+        st = stream()
+        _lib.call("gprb_add_noise", ptr(K), N, N, NE, float(noise_e), float(noise_f), st)
+        _lib.call("gprb_chol_factor", ptr(K), N, N, st)
+        alpha = torch.as_tensor(self.y_train[:, 0], device="cuda").clone().contiguous()
+        _lib.call("gprb_chol_solve_vec", ptr(K), N, N, ptr(alpha), st)
+        return alpha
+
+    def set_K_inv(self):
+        """K^-1 = L^-T L^-1 (gaussianprocess.py:128-131), by cuSOLVER potri on device."""
+        if self._Kinv_dev is None:
+            N = self._L_dev.shape[0]
+            Kinv = torch.empty((N, N), dtype=F64, device="cuda")
+            _lib.call("gprb_chol_inverse", ptr(self._L_dev), N, N, ptr(Kinv), N, stream())
+            self._Kinv_dev = Kinv
+
+    def log_marginal_likelihood(self, params, eval_gradient=False, clone_kernel=False):
+        """
+        Log marginal likelihood and (optionally) its gradient w.r.t. the hyper-parameters
+        (GPML eq. 5.9; gaussianprocess.py:133-202).
+        """
+        require_cuda()
+        if self.noise_bounds is None:
+            noise_e, noise_f = self.noise_e, self.noise_f
+            kernel_params = params
+        else:
+            noise_e = params[-1]
+            noise_f = self.f_coef * noise_e
+            kernel_params = params[:-1]
+        kernel = self.kernel
+        kernel.update(kernel_params)
+
+        is_rbf = isinstance(kernel, RBF_mb)
+        K, dK, shard = self._build_K(grad=eval_gradient)
+        N = K.shape[0]
+        NE = self._n_energy_rows()
+        st = stream()
+        try:
+            alpha = self._factor(K, noise_e, noise_f)
+        except _lib.NotPositiveDefinite:
+            return (-np.inf, np.zeros_like(params)) if eval_gradient else -np.inf
+
+        y = torch.as_tensor(self.y_train[:, 0], device="cuda")
+        terms = (ctypes_double * 2)()
+        _lib.call("gprb_lml_terms", ptr(K), N, N, ptr(y), ptr(alpha), terms, st)
+        logdet, ya = terms[0], terms[1]
+        MLL = -0.5 * ya - logdet - N / 2 * np.log(2 * np.pi)
+        if not eval_gradient:
+            return MLL
+
+        Kinv = torch.empty((N, N), dtype=F64, device="cuda")
+        _lib.call("gprb_chol_inverse", ptr(K), N, N, ptr(Kinv), N, st)
+        out = (ctypes_double * 2)()
+        # rows of dK held by this rank
+        if shard is None:
+            r_ranges = [(0, N)]
+        else:
+            windows, _ = shard
+            (e0, e1), (f0, f1) = windows[gdist.world()[0]]
+            r_ranges = [(e0, e1), (NE + 3 * f0, NE + 3 * f1)]
+        # 1/2 tr(W dK/dl) over my rows + 1/2 sum_i W_ii noise_i^2 (for the sigma term)
+        g_l = 0.0
+        half_w_noise = 0.0
+        half_w_base = 0.0
+        off = 0
+        for (r0, r1) in r_ranges:
+            if r1 > r0:
+                dptr = c_vp(0)
+                if is_rbf:
+                    dptr = c_vp(dK.data_ptr() + off * dK.shape[1] * 8)
+                _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, dptr, N, NE,
+                          float(noise_e) ** 2, float(noise_f) ** 2, out, st)
+                g_l += out[0]
+                half_w_noise += out[1]
+                _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, c_vp(0), N, NE,
+                          2.0 * float(noise_e), 2.0 * float(noise_f), out, st)
+                half_w_base += out[1]
+            off += r1 - r0
+        g_s0 = 0.0
+        if not is_rbf:
+            # Dot: dK/dsigma0 = 0.8 * 2 sigma^2 sigma0 on the E-E block only (dot_kernel.py:58)
+            (r0, r1) = r_ranges[0]
+            if r1 > r0 and NE > 0:
+                _lib.call("gprb_w_block_sum", N, r0, r1, 0, NE, ptr(alpha), ptr(Kinv), N, out, st)
+                g_s0 = out[0] * (0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0)
+        if shard is not None:
+            g_l, half_w_noise, half_w_base, g_s0 = gdist.all_reduce_sum([g_l, half_w_noise, half_w_base, g_s0], device="cuda")
+        # 1/2 tr(W (2/sigma) K0), K0 = K - noise:  tr(W K) = y.alpha - N
+        g_sigma = ((ya - N) - 2.0 * half_w_noise) / kernel.sigma
+        llg = np.array([g_sigma, g_l if is_rbf else g_s0, half_w_base])
+        if self.noise_bounds is None:
+            llg = llg[:-1]
+        return MLL, llg
+
+    def optimize(self, fun, theta0, bounds, maxiter=10):
+        """L-BFGS-B on the host, identical options to gaussianprocess.py:215-219."""
+        opt_res = minimize(fun, theta0, method="L-BFGS-B", bounds=bounds, jac=True,
+                           options={'maxiter': maxiter, 'ftol': 1e-2})
+        return opt_res.x, opt_res.fun
+
+    def fit(self, TrainData=None, show=True, opt=True, maxiter=10):
+        """
+        Fit the GPR model (gaussianprocess.py:222-317).
+
+        Args:
+            TrainData: a dictionary of energy/force/db data
+            show: print the information or not
+            opt: optimize the hyperparameters or not
+            maxiter: maximum number of L-BFGS-B iterations
+        """
+        require_cuda()
+        if TrainData is None:
+            self.update_y_train()
+        else:
+            self.set_train_pts(TrainData)
+
+        if self.rank == 0 and show:
+            print(self)
+
+        def obj_func(params, eval_gradient=True):
+            if eval_gradient:
+                lml, grad = self.log_marginal_likelihood(params, eval_gradient=True, clone_kernel=False)
+                if show:
+                    strs = "Loss: {:12.3f} ".format(-lml)
+                    for para in params:
+                        strs += "{:6.3f} ".format(para)
+                    if self.rank == 0:
+                        print(strs)
+                        self.logging.info(strs)
+                return (-lml, -grad)
+            lml = self.log_marginal_likelihood(params, clone_kernel=False)
+            return -lml
+
+        hyper_params = self.kernel.parameters()
+        hyper_bounds = list(self.kernel.bounds)
+        if self.noise_bounds is not None:
+            hyper_params += [self.noise_e]
+            hyper_bounds += [self.noise_bounds]
+
+        if opt:
+            if self.rank == 0:
+                print(f"Update GP model => {self.N_queue}/{maxiter}")
+            params, _ = self.optimize(obj_func, hyper_params, hyper_bounds, maxiter=maxiter)
+            if self.noise_bounds is not None:
+                self.kernel.update(params[:-1])
+                self.noise_e = params[-1]
+                self.noise_f = self.f_coef * params[-1]
+            else:
+                self.kernel.update(params)
+
+        # final covariance with the pair-cut variant of K_ff (f_tol = 1e-10), as k_total at :286
+        K, _, _ = self._build_K(grad=False)
+        self._alpha_dev = self._factor(K, self.noise_e, self.noise_f)
+        self._L_dev = K
+        self.logging.info("Cholesky Decomp is Complete")
+        self._Kinv_dev = None
+
+        self.N_energy_queue = 0
+        self.N_forces_queue = 0
+        self.N_queue = 0
+        self.fits += 1
+        self.set_K_inv()
+
+    def _predict_device(self, X, train_x, f_tol, return_std):
+        """K* on device, mean and variance (gaussianprocess.py:338, 368-377 / 880, 904-908)."""
+        K_trans, _ = self.kernel.k_total_device(X, train_x, f_tol=f_tol, grad=False)
+        m, N = K_trans.shape
+        mean = torch.empty(m, dtype=F64, device="cuda")
+        var = diag = work = None
+        if return_std:
+            diag = self.kernel.diag_device(X)
+            var = torch.empty(m, dtype=F64, device="cuda")
+            work = torch.empty((m, N), dtype=F64, device="cuda")
+            self.set_K_inv()
+        _lib.call("gprb_predict", m, N, ptr(K_trans), N, ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
+                  ptr(diag), ptr(mean), ptr(var), ptr(work), stream())
+        return K_trans, mean, var
+
+    def predict(self, X, stress=False, total_E=False, return_std=False, return_cov=False):
+        """
+        Predict energy/force rows for packed or listed data `X` (gaussianprocess.py:319-379).
+        """
+        require_cuda()
+        if stress:
+            raise NotImplementedError("stress prediction is not part of the B200 hot path yet (SURVEY.md §8f)")
+        train_x = self.get_train_x()
+        K_trans, mean, var = self._predict_device(X, train_x, 1e-10, return_std and not return_cov)
+        y_mean = mean.cpu().numpy()
+
+        Npts = 0
+        if 'energy' in X:
+            Npts += len(X["energy"][-1]) if isinstance(X["energy"], tuple) else len(X["energy"])
+        if 'force' in X:
+            Npts += 3 * len(X["force"][-1]) if isinstance(X["force"], tuple) else 3 * len(X["force"])
+        factors = np.ones(Npts)
+        if total_E:
+            if isinstance(X["energy"], tuple):
+                N_atoms = np.array([x for x in X["energy"][-1]])
+            else:
+                N_atoms = np.array([len(x) for x in X["energy"]])
+            factors[:len(N_atoms)] = N_atoms
+        y_mean *= factors
+
+        if return_cov:
+            # y_cov = k(X, X) - K* K^-1 K*^T   (:363-366)
+            self.set_K_inv()
+            Kxx, _ = self.kernel.k_total_device(X, None, grad=False)
+            y_cov = Kxx - K_trans @ (self._Kinv_dev @ K_trans.T)
+            return y_mean, y_cov.cpu().numpy()
+        elif return_std:
+            return y_mean, np.sqrt(var.cpu().numpy()) * factors
+        return y_mean
+
+    # ---------------------------------------------------------------------------------------------
+    # training-set bookkeeping (host; identical semantics to gaussianprocess.py:381-629)
+    # ---------------------------------------------------------------------------------------------
+    def set_train_pts(self, data, mode="w"):
+        """Set ("w") or append ("a+") training points from {'energy','force','db'} lists (:381-425)."""
+        if mode == "w" or self.train_x is None:
+            self.train_x = {'energy': [], 'force': []}
+            self.train_y = {'energy': [], 'force': []}
+            self.train_db = []
+
+        N_E, N_F = 0, 0
+        for d in data["db"]:
+            (atoms, energy, force, energy_in, force_in) = d
+            if energy_in:
+                e_id = N_E + 1
+                N_E += 1
+            else:
+                e_id = None
+            if len(force_in) > 0:
+                f_ids = [N_F + i for i in range(len(force_in))]
+                N_F += len(force_in)
+            else:
+                f_ids = []
+            self.train_db.append((atoms, energy, force, energy_in, force_in, e_id, f_ids))
+
+        for key in data.keys():
+            if key == 'energy' and len(data[key]) > 0:
+                self.add_train_pts_energy(data[key])
+            elif key == 'force' and len(data[key]) > 0:
+                self.add_train_pts_force(data[key])
+
+        self.update_y_train()
+        self.N_energy += N_E
+        self.N_forces += N_F
+        self.N_energy_queue += N_E
+        self.N_forces_queue += N_F
+        self.N_queue += N_E + N_F
+
+    def remove_train_pts(self, e_ids, f_ids):
+        """Delete training points and refit (:427-464)."""
+        data = {"energy": [], "force": [], "db": []}
+        energy_data = tuple_to_list(self.train_x['energy'], mode='energy')
+        force_data = tuple_to_list(self.train_x['force'])
+        for i, (X, ele) in enumerate(energy_data):
+            if i not in e_ids:
+                data['energy'].append((X, self.train_y['energy'][i], ele))
+        for i, (X, dxdr, ele) in enumerate(force_data):
+            if i not in f_ids:
+                data["force"].append((X, dxdr, self.train_y['force'][i], ele))
+        for (atoms, energy, force, energy_in, force_in, e_id, _f_ids) in self.train_db:
+            if e_id in e_ids:
+                energy_in = False
+            _force_in = [force_in[i] for i, f_id in enumerate(_f_ids) if f_id not in f_ids]
+            if energy_in or len(_force_in) > 0:
+                data['db'].append((atoms, energy, force, energy_in, _force_in))
+        self.N_energy = self.N_forces = 0
+        self.N_energy_queue = self.N_forces_queue = self.N_queue = 0
+        self.set_train_pts(data)
+        self.fit()
+
+    def compute_base_potential(self, atoms):
+        return self.base_potential.calculate(atoms)
+
+    def update_y_train(self):
+        """Targets as one column: per-atom energies, then (Fx, Fy, Fz) per force centre (:472-488)."""
+        E = np.asarray(self.train_y["energy"], dtype=np.float64).reshape(-1)
+        F = np.asarray(self.train_y["force"], dtype=np.float64).reshape(-1)
+        self.y_train = np.concatenate((E, F)).reshape(-1, 1)
+
+    def validate_data(self, test_data=None, total_E=False, return_std=False, show=False):
+        """Predict a labelled data set (default: the training set) (:490-535)."""
+        if test_data is None:
+            test_X_E = {"energy": self.train_x['energy']}
+            test_X_F = {"force": self.train_x['force']}
+            NE = len(test_X_E['energy'][-1]) if len(test_X_E['energy']) > 0 else 0
+            E = self.y_train[:NE].flatten()
+            F = self.y_train[NE:].flatten()
+        else:
+            test_X_E = {"energy": [(data[0], data[2]) for data in test_data['energy']]}
+            test_X_F = {"force": [(data[0], data[1], data[3]) for data in test_data['force']]}
+            E = np.array([data[1] for data in test_data['energy']])
+            F = np.array([data[2] for data in test_data['force']]).flatten()
+
+        if total_E:
+            for i in range(len(E)):
+                E[i] *= len(test_X_E['energy'][i])
+
+        E_Pred, E_std, F_Pred, F_std = None, None, None, None
+        if return_std:
+            if len(test_X_E['energy']) > 0:
+                E_Pred, E_std = self.predict(test_X_E, total_E=total_E, return_std=True)
+            if len(test_X_F['force']) > 0:
+                F_Pred, F_std = self.predict(test_X_F, return_std=True)
+            if show:
+                self.update_error(E, E_Pred, F, F_Pred)
+            return E, E_Pred, E_std, F, F_Pred, F_std
+        if len(test_X_E['energy']) > 0:
+            E_Pred = self.predict(test_X_E, total_E=total_E)
+        if len(test_X_F['force']) > 0:
+            F_Pred = self.predict(test_X_F)
+        if show:
+            self.update_error(E, E_Pred, F, F_Pred)
+        return E, E_Pred, F, F_Pred
+
+    def update_error(self, E, E_Pred, F, F_Pred):
+        e_r2, e_mae, e_rmse = metric_values(E, E_Pred)
+        f_r2, f_mae, f_rmse = metric_values(F, F_Pred)
+        self.error = {"energy_r2": e_r2, "energy_mae": e_mae, "energy_rmse": e_rmse,
+                      "forces_r2": f_r2, "forces_mae": f_mae, "forces_rmse": f_rmse}
+        if self.rank == 0:
+            for key in self.error.keys():
+                self.logging.info(f"{key:<12s}: {self.error[key]:.4f}")
+
+    def get_train_x(self):
+        """Training data without the not-yet-fitted queue (:553-577)."""
+        if self.N_queue > 0:
+            train_x = {}
+            (_X, _ELE, _indices) = self.train_x['energy']
+            NE = self.N_energy - self.N_energy_queue
+            if NE > 0:
+                ids = sum(_indices[:NE])
+                train_x['energy'] = (_X[:ids], _ELE[:ids], _indices[:NE])
+            else:
+                train_x['energy'] = (_X, _ELE, _indices)
+            NF = self.N_forces - self.N_forces_queue
+            (_X, _dXdR, _ELE, _indices) = self.train_x['force']
+            if NF > 0:
+                ids = sum(_indices[:NF])
+                train_x['force'] = (_X[:ids], _dXdR[:ids], _ELE[:ids], _indices[:NF])
+            else:
+                train_x['force'] = (_X, _dXdR, _ELE, _indices)
+            return train_x
+        return self.train_x
+
+    def add_train_pts_energy(self, energy_data):
+        """Append (x, E/atom, ele) items to the packed energy set (:579-600)."""
+        (X, ELE, indices, E) = list_to_tuple(energy_data, include_value=True, mode='energy')
+        if len(self.train_x['energy']) == 3:
+            (_X, _ELE, _indices) = self.train_x['energy']
+            self.train_x['energy'] = (np.concatenate((_X, X), axis=0), np.concatenate((_ELE, ELE), axis=0),
+                                      list(_indices) + list(indices))
+            self.train_y['energy'] = list(self.train_y['energy']) + list(E)
+        else:
+            self.train_x['energy'] = (X, ELE, indices)
+            self.train_y['energy'] = E
+
+    def add_train_pts_force(self, force_data):
+        """Append (x, dxdr, F, ele) items to the packed force set (:602-629)."""
+        (X, dXdR, ELE, indices, F) = list_to_tuple(force_data, include_value=True)
+        if len(self.train_x['force']) == 4:
+            (_X, _dXdR, _ELE, _indices) = self.train_x['force']
+            self.train_x['force'] = (np.concatenate((_X, X), axis=0), np.concatenate((_dXdR, dXdR), axis=0),
+                                     np.concatenate((_ELE, ELE), axis=0), list(_indices) + list(indices))
+            self.train_y['force'] = list(self.train_y['force']) + list(F)
+        else:
+            self.train_x['force'] = (X, dXdR, ELE, indices)
+            self.train_y['force'] = F
+
+    # ---------------------------------------------------------------------------------------------
+    # persistence (json part only; the ASE-db part needs ASE — SURVEY.md §8f #2)
+    # ---------------------------------------------------------------------------------------------
+    def save_dict(self, db_filename):
+        noise = {"energy": self.noise_e, "force": self.noise_f, "f_coef": self.f_coef, "bounds": self.noise_bounds}
+        dict0 = {"noise": noise, "kernel": self.kernel.save_dict(), "descriptor": self.descriptor.save_dict(),
+                 "db_filename": db_filename}
+        if self.error is not None:
+            dict0["error"] = self.error
+        if self.base_potential is not None:
+            dict0["base_potential"] = self.base_potential.save_dict()
+        return dict0
+
+    def save(self, filename, db_filename, verbose=True):
+        with open(filename, "w") as fp:
+            json.dump(self.save_dict(db_filename), fp, indent=4)
+        self.export_ase_db(db_filename, permission="w")
+        if verbose:
+            print(f"save model to {filename} and {db_filename}")
+
+    def export_ase_db(self, db_filename, permission="w"):
+        try:
+            from ase.db import connect
+        except ImportError as exc:
+            raise ImportError("GP.export_ase_db needs ASE (ase.db); it is outside the B200 hot path") from exc
+        if permission == "w" and os.path.exists(db_filename):
+            os.remove(db_filename)
+        with connect(db_filename, serial=True) as db:
+            for (struc, energy, force, energy_in, force_in, _, _) in self.train_db:
+                actual_energy, actual_forces = deepcopy(energy), force.copy()
+                if self.base_potential is not None:
+                    energy_off, force_off, _ = self.compute_base_potential(struc)
+                    actual_energy += energy_off
+                    actual_forces += force_off
+                data = {"energy": energy, "force": force, "energy_in": energy_in, "force_in": force_in}
+                kvp = {"dft_energy": actual_energy / len(force), "dft_fmax": np.max(np.abs(actual_forces.flatten()))}
+                struc.set_constraint()
+                db.write(struc, data=data, key_value_pairs=kvp)
+
+    @classmethod
+    def load(cls, filename, N_max=None, device='cuda'):
+        with open(filename, "r") as fp:
+            dict0 = json.load(fp)
+        instance = cls.load_from_dict(dict0, device=device)
+        instance.extract_db(dict0["db_filename"], N_max)
+        if instance.rank == 0:
+            print(f"load GP model from {filename}")
+            print(instance)
+        return instance
+
+    def extract_db(self, db_filename, N_max=None):
+        """Recompute descriptors for the structures of an ASE database (:726-821)."""
+        try:
+            from ase.db import connect
+        except ImportError as exc:
+            raise ImportError("GP.extract_db needs ASE (ase.db); it is outside the B200 hot path") from exc
+        pts = {"energy": [], "force": [], "db": []}
+        with connect(db_filename, serial=True) as db:
+            for n, row in enumerate(db.select()):
+                if N_max is not None and n >= N_max:
+                    break
+                atoms = db.get_atoms(id=row.id)
+                energy, force = row.data.energy, row.data.force.copy()
+                energy_in, force_in = row.data.energy_in, row.data.force_in
+                d = self.descriptor.calculate(atoms)
+                ele = atomic_numbers(d['elements'])
+                if energy_in:
+                    pts["energy"].append((d['x'], energy / len(atoms), ele))
+                for i in force_in:
+                    x, dxdr, e = force_rows(d, ele, i)
+                    pts["force"].append((x, dxdr, force[i], e))
+                pts["db"].append((atoms, energy, force, energy_in, force_in))
+        self.N_energy = self.N_forces = 0
+        self.N_energy_queue = self.N_forces_queue = self.N_queue = 0
+        self.set_train_pts(pts, "w")
+
+    # ---------------------------------------------------------------------------------------------
+    # structure-level API
+    # ---------------------------------------------------------------------------------------------
+    def _get_fixed_atoms(self, struc):
+        """Indices held by a FixAtoms-like constraint (anything exposing get_indices) (:823-832)."""
+        for c in getattr(struc, "constraints", []) or []:
+            if type(c).__name__ == "FixAtoms" and hasattr(c, "get_indices"):
+                return list(c.get_indices())
+        return []
+
+    def predict_structure(self, struc, stress=True, return_std=False, f_tol=1e-8):
+        """
+        Energy, forces (and their standard deviations) of one structure (:834-918).
+
+        Note: the reference's default stress=True needs the stress covariance blocks, which are
+        not part of the B200 hot path yet; pass stress=False (what GPR.calculate does by default,
+        calculator.py:124-127).
+        """
+        require_cuda()
+        if stress:
+            raise NotImplementedError("stress prediction is not part of the B200 hot path yet (SURVEY.md §8f); "
+                                      "call predict_structure(struc, stress=False, ...)")
+        d = self.descriptor.calculate(struc, use_mpi=True)
+        ele = atomic_numbers(d['elements'])
+        fix_ids = self._get_fixed_atoms(struc)
+        free_ids = [i for i in range(len(struc)) if i not in set(fix_ids)]
+        data = {"energy": list_to_tuple([(d['x'], ele)], mode='energy')}
+        data["force"] = [force_rows(d, ele, i) for i in free_ids]
+        if len(free_ids) == 0:
+            del data["force"]
+
+        train_x = self.get_train_x()
+        _, mean, var = self._predict_device(data, train_x, f_tol, return_std)
+        y_mean = mean.cpu().numpy()
+        y_mean[0] *= len(struc)
+        E = y_mean[0]
+        F = np.zeros((len(struc), 3))
+        F[free_ids] = y_mean[1:].reshape([len(free_ids), 3])
+        S = None
+
+        if self.base_potential is not None:
+            energy_off, force_off, _ = self.compute_base_potential(struc)
+            E += energy_off
+            F += force_off
+
+        if return_std:
+            y_std = np.sqrt(var.cpu().numpy())
+            E_std = y_std[0]
+            F_std = np.zeros((len(struc), 3))
+            F_std[free_ids] = y_std[1:].reshape([len(free_ids), 3])
+            return E, F, S, E_std, F_std
+        return E, F, S
+
+    def add_structure(self, data, N_max=20, tol_e_var=1.2, tol_f_var=1.2, add_force=True):
+        """
+        Add training points from a labelled structure (:921-1002): the energy always; up to N_max
+        force centres whose predicted std or error exceeds the tolerance and whose descriptor is
+        new (utilities.new_pt).
+        """
+        tol_e_var *= self.noise_e
+        tol_f_var *= self.noise_f
+        pts_to_add = {"energy": [], "force": [], "db": []}
+        (atoms, energy, force) = data
+
+        if self.base_potential is not None:
+            energy_off, force_off, _ = self.compute_base_potential(atoms)
+        else:
+            energy_off, force_off = 0, np.zeros((len(atoms), 3))
+        energy = energy - energy_off
+        force = force - force_off
+        my_data = convert_train_data([(atoms, energy, force)], self.descriptor)
+
+        if self._alpha_dev is not None:
+            E, E1, E_std, F, F1, F_std = self.validate_data(my_data, return_std=True)
+            E_std = E_std[0]
+            F_std = F_std.reshape((len(atoms), 3))
+        else:
+            E = E1 = [energy / len(atoms)]
+            F = F1 = force.flatten()
+            E_std = 2 * tol_e_var
+            F_std = 2 * tol_f_var * np.ones((len(atoms), 3))
+        # NOTE: F and F1 stay FLAT (3n,) and are indexed by atom id below, exactly as the reference
+        # does (gaussianprocess.py:979) — this decides which force centres enter the training set.
+        F, F1 = np.asarray(F), np.asarray(F1)
+
+        pts_to_add["energy"] = my_data["energy"]
+        N_energy, energy_in = 1, True
+
+        force_in = []
+        if add_force:
+            xs_added = []
+            for f_id in range(len(atoms)):
+                include = False
+                if np.max(F_std[f_id]) > tol_f_var or np.max(abs(F[f_id] - F1[f_id])) > 1.5 * tol_f_var:
+                    X = my_data["energy"][0][0][f_id]
+                    _ele = my_data["energy"][0][2][f_id]
+                    if len(xs_added) == 0 or new_pt((X, _ele), xs_added):
+                        include = True
+                if include:
+                    force_in.append(f_id)
+                    xs_added.append((X, _ele))
+                    pts_to_add["force"].append(my_data["force"][f_id])
+                if len(force_in) == N_max:
+                    break
+
+        N_pts = N_energy + len(force_in)
+        if N_pts > 0:
+            pts_to_add["db"].append((atoms, energy, force, energy_in, force_in))
+            self.set_train_pts(pts_to_add, mode="a+")
+        errors = (E[0] + energy_off, E1[0] + energy_off, E_std,
+                  F + force_off.flatten(), F1 + force_off.flatten(), F_std)
+        return pts_to_add, N_pts, errors
+
+    def sparsify(self, e_tol=1e-10, f_tol=1e-10):
+        """Drop training points in the near-null space of K (CUR, :1004-1023)."""
+        K = self.kernel.k_total(self.train_x)
+        N_e = len(self.train_x["energy"][-1])
+        N_f = len(self.train_x["force"][-1])
+        pts_e = CUR(K[:N_e, :N_e], e_tol)
+        pts = CUR(K[N_e:, N_e:], f_tol)
+        pts_f = []
+        if N_f > 1:
+            for i in range(N_f):
+                if all(np.sum(pts == i * 3 + c) == 1 for c in range(3)):
+                    pts_f.append(i)
+        print("{:d} energy and {:d} forces will be removed".format(len(pts_e), len(pts_f)))
+        if len(pts_e) + len(pts_f) > 0:
+            self.remove_train_pts(pts_e, pts_f)
+
+    @classmethod
+    def set_GPR(cls, images, base, kernel='RBF',
+                zeta=2.0, noise_e=0.002, noise_f=0.1,
+                lmax=4, nmax=3, rcut=5.0, json_file=None,
+                overwrite=False):
+        """Set up and train a GPR model from images with a base calculator (:1025-1072)."""
+        if json_file is not None and os.path.exists(json_file):
+            instance = cls.load(json_file)
+            if overwrite:
+                instance.noise_e = noise_e
+                instance.noise_f = noise_f
+                if instance.kernel.name != kernel:
+                    if kernel == "RBF":
+                        instance.kernel = RBF_mb(para=[1.0, 0.1], zeta=zeta)
+                    else:
+                        instance.kernel = Dot_mb(para=[2, 2.0], zeta=zeta)
+            instance.fit()
+            instance.set_K_inv()
+        else:
+            instance = cls(kernel=None, descriptor=None, base_potential=None)
+            if kernel == 'Dot':
+                instance.kernel = Dot_mb(para=[2, 2.0], zeta=zeta)
+            else:
+                instance.kernel = RBF_mb(para=[1.0, 0.1], zeta=zeta)
+            instance.descriptor = _lazy_SO3()(nmax=nmax, lmax=lmax, rcut=rcut)
+            instance.noise_e = noise_e
+            instance.noise_f = noise_f
+            instance.train_images(images, base)
+        return instance
+
+    def train_images(self, images, base):
+        """Label the images with the base calculator, add them and fit (:1074-1116)."""
+        for i, image in enumerate(images):
+            image.calc = base
+            if hasattr(image.calc, 'set'):
+                image.calc.set(directory=f"GP/calc_{i}")
+            eng = image.get_potential_energy()
+            forces = image.get_forces()
+            if self.rank == 0:
+                print(f"Calculate E/F for image {i}: {eng:.6f}")
+            image.calc = None
+            self.add_structure((image.copy(), eng, forces))
+        self.fit()
+        self.validate_data()
+        self.set_K_inv()
+
+    @classmethod
+    def load_from_dict(cls, dict0, device='cuda'):
+        """Rebuild kernel, descriptor and noise settings from a saved dictionary (:1118-1161)."""
+        instance = cls(kernel=None, descriptor=None, base_potential=None)
+        if dict0["kernel"]["name"] in ["RBF", "RBF_mb"]:
+            instance.kernel = RBF_mb()
+        elif dict0["kernel"]["name"] in ["Dot", "Dot_mb"]:
+            instance.kernel = Dot_mb()
+        else:
+            raise NotImplementedError("unknown kernel {:s}".format(dict0["kernel"]["name"]))
+        instance.kernel.load_from_dict(dict0["kernel"])
+
+        if dict0["descriptor"]["_type"] == "SO3":
+            instance.descriptor = _lazy_SO3()()
+            instance.descriptor.load_from_dict(dict0["descriptor"])
+        else:
+            raise NotImplementedError("unknown descriptors {:s}".format(str(dict0["descriptor"].get("name"))))
+
+        if "base_potential" in dict0.keys():
+            raise NotImplementedError("base potentials are outside the B200 hot path (SURVEY.md §2.1 #13)")
+        instance.kernel.device = device
+        instance.noise_e = dict0["noise"]["energy"]
+        instance.noise_f = dict0["noise"]["force"]
+        instance.f_coef = dict0["noise"]["f_coef"]
+        instance.noise_bounds = dict0["noise"]["bounds"]
+        return instance
+
+
+import ctypes  # noqa: E402
+
+ctypes_double = ctypes.c_double
+
+
+def CUR(K, l_tol=1e-10):
+    """CUR selection of the rows most aligned with the near-null space of K
+    (Jinnouchi et al., PRB 100, 014105 (2019), App. D; gaussianprocess.py:1165-1182)."""
+    L, U = np.linalg.eigh(K)
+    low = L < l_tol
+    omega = (U[:, low] ** 2).sum(axis=1)
+    ids = np.argsort(-1 * omega)
+    return ids[:int(low.sum())]

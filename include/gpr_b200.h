@@ -127,6 +127,31 @@ int gprb_predict(int m, int N, const double *Ks_dev, long long ldks, const doubl
                  const double *Kinv_dev, long long ldi, const double *diag_dev,
                  double *mean_dev, double *var_dev, double *work_dev, void *stream);
 
+/* ---- SO(3) power-spectrum descriptor (gpr_calc/SO3.py:186-727), batched over structures --------
+ * Atoms of all structures are concatenated; atom_ptr[S+1] gives the first atom of each structure,
+ * struct_of[n_atoms] the structure of each atom.  All pointers are device pointers.
+ *
+ * gprb_so3_neighbors : replaces SO3.build_neighbor_list (SO3.py:348-407) and the un-vendored
+ *   ase.neighborlist.NeighborList it calls (:357-363): all (i, j, S) with |r_j + S.cell - r_i| < rcut
+ *   except (i, i, 0); nimg[S,3] = images searched per axis (0 on non-periodic axes).
+ *   mode 0 counts: nnb[i] neighbours and nuniq[i] = |{j} U {i}| rows of `seq`;
+ *   mode 1 fills nb_j / nb_rvec at nb_ptr[i] (exclusive scan of nnb), sorted by (j, S).
+ * gprb_so3_radial    : radial integrals of compute_dcs (SO3.py:619-652) per neighbour,
+ *   rad[w] = { I[nmax][lmax+1], dI/dr[nmax][lmax+1] }; rho[nq], G[nmax,nq] are the quadrature
+ *   nodes and the combined weights g_n(rho) rho^2 e^{-a rho^2} sqrt(1-t^2) w (SO3.py:633,646-647).
+ * gprb_so3_power     : c_nlm, power spectrum x[n_atoms,d], dxdr[n_seq,d,3] and seq[n_seq,2] (int64,
+ *   atom indices local to the structure) (SO3.py:243-273, 655-727); seq_ptr = exclusive scan of nuniq. */
+int gprb_so3_neighbors(int n_struct, int n_atoms, const int *atom_ptr, const int *struct_of,
+                       const double *pos, const double *cell, const int *nimg, double rcut,
+                       int mode, int *nnb, int *nuniq, const int *nb_ptr, int *nb_j, double *nb_rvec,
+                       void *stream);
+int gprb_so3_radial(int n_nb, const double *nb_rvec, int nmax, int lmax, int nq, double alpha, double rcut,
+                    const double *rho, const double *G, double *rad, void *stream);
+int gprb_so3_power(int n_atoms, const int *nb_ptr, const int *nb_j, const double *nb_rvec, const double *rad,
+                   const int *numbers, const int *atom_ptr, const int *struct_of, const int *seq_ptr,
+                   int nmax, int lmax, double alpha, double rcut, const double *norm_l, int derivative,
+                   double *x, double *dxdr, long long *seq, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
