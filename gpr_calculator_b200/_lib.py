@@ -20,7 +20,7 @@ SIGNATURES = {
     "gprb_version": (c_int, []),
     "gprb_last_error": (ctypes.c_char_p, []),
     "gprb_device_info": (c_int, [c_int_p, c_int_p, c_int_p]),
-    "gprb_pack_create": (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "gprb_pack_create": (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_dbl, c_vp]),
     "gprb_pack_destroy": (None, [c_vp]),
     "gprb_pack_info": (c_int, [c_vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "gprb_pack_pair_count": (c_ll, [c_vp, c_int, c_int, c_vp]),

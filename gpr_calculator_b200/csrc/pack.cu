@@ -33,7 +33,7 @@ extern "C" int gprb_device_info(int *sm_count, int *cc_major, int *cc_minor) {
 }
 
 // One warp per padded row.  HBM-bound: reads 8*d*(1+ncols) bytes and writes 8*4ks*(1+ncols) per row.
-__global__ void prep_rows_kernel(int n_padded, int d, int ncols, int ks,
+__global__ void prep_rows_kernel(int n_padded, int d, int ncols, int ks, double norm_eps,
                                  const double *__restrict__ x, const double *__restrict__ dxdr,
                                  const int *__restrict__ ele, const int *__restrict__ src_row,
                                  double *__restrict__ P, double *__restrict__ norm_out,
@@ -57,8 +57,8 @@ __global__ void prep_rows_kernel(int n_padded, int d, int ncols, int ks,
     for (int k = lane; k < d; k += 32) { double v = xr[k]; ss += v * v; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const double n = sqrt(ss);
-    const bool dropped = !(n > GPRB_EPS_NORM);
+    const double n = sqrt(ss) + norm_eps;
+    const bool dropped = (norm_eps == 0.0) && !(n > GPRB_EPS_NORM);
     const double inv = dropped ? 0.0 : 1.0 / n;
     // t_c = x^ . A[:,c]
     double t[9];
@@ -81,7 +81,7 @@ __global__ void prep_rows_kernel(int n_padded, int d, int ncols, int ks,
         }
     }
     if (lane == 0) {
-        norm_out[warp] = n;
+        norm_out[warp] = n - norm_eps;
         const int z = ele[src];
         elep[warp] = dropped ? -(z + 2) : z;
     }
@@ -113,12 +113,14 @@ extern "C" void gprb_pack_destroy(gprb_pack *p) {
 }
 
 extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_rows_host, int d, int ncols,
-                                const double *x_any, const double *dxdr_any, const int *ele_any, void *stream) {
+                                const double *x_any, const double *dxdr_any, const int *ele_any, double norm_eps,
+                                void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(out != nullptr, "gprb_pack_create: out is NULL");
     *out = nullptr;
     GPRB_REQUIRE(n_groups >= 0 && d > 0, "gprb_pack_create: bad sizes n_groups=%d d=%d", n_groups, d);
     GPRB_REQUIRE(ncols == 0 || ncols == 3, "gprb_pack_create: ncols must be 0 (energy) or 3 (force), got %d", ncols);
+    GPRB_REQUIRE(norm_eps >= 0.0, "gprb_pack_create: norm_eps must be >= 0");
     GPRB_REQUIRE(ncols == 0 || dxdr_any != nullptr || n_groups == 0, "gprb_pack_create: dxdr is NULL for a force pack");
     gprb_pack *p = new gprb_pack();
     GPRB_CUDA(cudaGetDevice(&p->device));
@@ -187,7 +189,7 @@ extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_
     {
         const int threads = 256, wpb = threads / 32;
         const int blocks = (n_padded + wpb - 1) / wpb;
-        prep_rows_kernel<<<blocks, threads, 0, st>>>(n_padded, d, ncols, p->ks, dx, ddx, de, d_src,
+        prep_rows_kernel<<<blocks, threads, 0, st>>>(n_padded, d, ncols, p->ks, norm_eps, dx, ddx, de, d_src,
                                                      p->P, p->norm, p->elep);
         PK_CUDA(cudaGetLastError());
     }

@@ -42,7 +42,7 @@ class Pack:
     torch CUDA tensors.
     """
 
-    def __init__(self, x, ele, indices, dxdr=None):
+    def __init__(self, x, ele, indices, dxdr=None, norm_eps=0.0):
         require_cuda()
         self.handle = c_vp(0)
         keep = []
@@ -77,7 +77,8 @@ class Pack:
         self.indices = [int(v) for v in rows]
         _lib.call("gprb_pack_create", ctypes.byref(self.handle), c_int(len(rows)),
                   c_vp(rows.ctypes.data) if len(rows) else c_vp(0), c_int(d), c_int(self.ncols),
-                  as_ptr(x, np.float64, F64), as_ptr(dxdr, np.float64, F64), as_ptr(ele, np.int32, torch.int32), stream())
+                  as_ptr(x, np.float64, F64), as_ptr(dxdr, np.float64, F64), as_ptr(ele, np.int32, torch.int32),
+                  float(norm_eps), stream())
 
     def pair_count(self, other, g0=0, g1=None):
         g1 = self.n_groups if g1 is None else g1
@@ -149,7 +150,7 @@ def energy_pack(data):
     return Pack(X, ELE, indices)
 
 
-def force_pack(data):
+def force_pack(data, norm_eps=0.0):
     """`data`: packed tuple (X, dXdR, ELE, indices), or list / object ndarray of (x, dxdr, ele)."""
     if data is None:
         return None
@@ -159,12 +160,13 @@ def force_pack(data):
         X, dXdR, ELE, indices = data
         if len(indices) == 0:
             return None
-        return _cached(X, len(indices), lambda: Pack(X, ELE, indices, dxdr=dXdR[:, :, :3] if dXdR.shape[2] != 3 else dXdR))
+        build = lambda: Pack(X, ELE, indices, dxdr=dXdR[:, :, :3] if dXdR.shape[2] != 3 else dXdR, norm_eps=norm_eps)  # noqa: E731
+        return build() if norm_eps else _cached(X, len(indices), build)
     if len(data) == 0:
         return None
     from .utilities import list_to_tuple
     X, dXdR, ELE, indices = list_to_tuple(list(data), stress=False)
-    return Pack(X, ELE, indices, dxdr=dXdR)
+    return Pack(X, ELE, indices, dxdr=dXdR, norm_eps=norm_eps)
 
 
 def packs_of(data):

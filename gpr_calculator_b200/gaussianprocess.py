@@ -263,6 +263,7 @@ class GP():
         if not is_rbf:
             # Dot: dK/dsigma0 = 0.8 * 2 sigma^2 sigma0 on the E-E block only (dot_kernel.py:58)
             (r0, r1) = r_ranges[0]
+            r1 = min(r1, NE)            # energy rows held by this rank
             if r1 > r0 and NE > 0:
                 _lib.call("gprb_w_block_sum", N, r0, r1, 0, NE, ptr(alpha), ptr(Kinv), N, out, st)
                 g_s0 = out[0] * (0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0)

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..device import packs_of, k_total_device, diag_device
+from ..device import packs_of, k_total_device, diag_device, energy_pack, force_pack
 
 
 class Dot_mb():
@@ -60,7 +60,10 @@ class Dot_mb():
     def diag_device(self, data):
         if "force" in data and isinstance(data["force"], tuple):
             raise ValueError("Dot_mb.diag expects force data as a list of (x, dxdr, ele) (Dot_mb.py:71-78)")
-        return diag_device(_lib.DOT, float(self.sigma), float(self.sigma0), float(self.zeta), packs_of(data), tol=0.0)
+        # the numpy K_ff behind Dot_mb.diag regularises every norm with +1e-8 (Dot_mb.py:206-221)
+        e = energy_pack(data["energy"]) if "energy" in data else None
+        f = force_pack(data["force"], norm_eps=1e-8) if "force" in data else None
+        return diag_device(_lib.DOT, float(self.sigma), float(self.sigma0), float(self.zeta), (e, f), tol=0.0)
 
     # ---- reference API ------------------------------------------------------------------------
     def diag(self, data):

@@ -193,3 +193,13 @@ class SimpleAtoms:
 
     def copy(self):
         return SimpleAtoms(self.numbers, self.positions, self.cell, self.pbc, self.constraints)
+
+
+class FixAtoms:
+    """Stand-in for ase.constraints.FixAtoms (only get_indices is used, gaussianprocess.py:823-832)."""
+
+    def __init__(self, indices):
+        self.index = np.asarray(indices, dtype=int)
+
+    def get_indices(self):
+        return self.index

@@ -50,9 +50,12 @@ int gprb_device_info(int *sm_count, int *cc_major, int *cc_minor);
  *   ncols = 3 : force rows (x, dxdr[.,d,3])   -> tiles of [x^; A~_x; A~_y; A~_z]
  * with x^ = x/|x| and A~ = (I - x^ x^T) dxdr / |x|.  Rows with |x| <= 1e-8 are dropped as in
  * rbf_kernel.cpp:26,37.  group_rows_host[g] = number of rows of group g (the `indices` list).
- * x_any/dxdr_any/ele_any may be host or device pointers. */
+ * x_any/dxdr_any/ele_any may be host or device pointers.
+ * norm_eps = 0 is the covariance convention.  norm_eps > 0 replaces |x| by |x| + norm_eps everywhere
+ * and drops nothing: the convention of the numpy K_ff that Dot_mb.diag alone uses (Dot_mb.py:204-221). */
 int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_rows_host, int d, int ncols,
-                     const double *x_any, const double *dxdr_any, const int *ele_any, void *stream);
+                     const double *x_any, const double *dxdr_any, const int *ele_any, double norm_eps,
+                     void *stream);
 void gprb_pack_destroy(gprb_pack *p);
 int gprb_pack_info(const gprb_pack *p, int *n_groups, int *n_rows, int *d, int *ncols, int *n_tiles);
 /* number of same-species, non-dropped row pairs between groups [g0,g1) of a and all groups of b

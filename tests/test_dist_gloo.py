@@ -1,0 +1,58 @@
+"""CPU, world_size 2, gloo: the row-block gather / scalar all-reduce logic of the multi-GPU path."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, size, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    from gpr_calculator_b200 import dist as gd
+    NE, NF = 5, 11
+    N = NE + 3 * NF
+    full = torch.arange(N * N, dtype=torch.float64).reshape(N, N)
+    windows = gd.row_windows([10] * NE, list(range(20, 20 + NF)), size)
+    (e0, e1), (f0, f1) = windows[rank]
+    local = torch.cat((full[e0:e1], full[NE + 3 * f0:NE + 3 * f1]))
+    got = gd.gather_rows(local, windows, NE, N)
+    ok = bool(torch.equal(got, full))
+    s = gd.all_reduce_sum([float(rank + 1), 2.0])
+    q.put((rank, ok, s, gd.world()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gather_rows_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, ok, s, w in res:
+        assert ok, "rank %d reassembled a wrong matrix" % rank
+        assert s == [3.0, 4.0] and w == (rank, 2)
+
+
+def test_single_rank_is_identity():
+    from gpr_calculator_b200 import dist as gd
+    K = torch.ones((4, 4), dtype=torch.float64)
+    assert gd.gather_rows(K, [((0, 1), (0, 1))], 1, 4) is K
+    assert gd.all_reduce_sum([1.5]) == [1.5] and gd.world() == (0, 1)

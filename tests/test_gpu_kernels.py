@@ -1,0 +1,192 @@
+"""GPU parity: covariance blocks of libgpr_b200 (through the C-ABI, via the reference-shaped wrappers)
+against the golden vectors of the reference and the CPU oracle.  Tolerance from north_star:
+K entries within 1e-10 relative (of the block's largest entry: entries that are sums of cancelling
+terms are compared on the block scale)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_force, make_energy, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gk():
+    return np.load(os.path.join(GOLD, "kernels.npz"))
+
+
+def _inputs(g):
+    F1 = (g["F1_x"], g["F1_dxdr"], g["F1_ele"], list(g["F1_ind"]))
+    F2 = (g["F2_x"], g["F2_dxdr"], g["F2_ele"], list(g["F2_ind"]))
+    E1 = (g["E1_x"], g["E1_ele"], list(g["E1_ind"]))
+    E2 = (g["E2_x"], g["E2_ele"], list(g["E2_ind"]))
+    return E1, E2, F1, F2
+
+
+def test_library_loaded_and_device_is_blackwell():
+    from gpr_calculator_b200 import _lib
+    import ctypes
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.call("gprb_device_info", ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr))
+    assert sm.value > 0 and maj.value >= 10
+
+
+def test_rbf_blocks_vs_golden(gk):
+    from gpr_calculator_b200.kernels import rbf_kernel as rk
+    E1, E2, F1, F2 = _inputs(gk)
+    sig, l = gk["params"]
+    for zeta in (2.0, 3.0):
+        z = "z%d" % int(zeta)
+        assert rel_err(rk.kee_C(E1, E2, sig, l, zeta), gk["rbf_kee_" + z]) <= TOL
+        assert rel_err(rk.kef_C(E1, F2, sig, l, zeta), gk["rbf_kef_" + z]) <= TOL
+        assert rel_err(rk.kff_C(F1, F2, sig, l, zeta, tol=1e-12), gk["rbf_kff_" + z]) <= TOL
+        for name, fn, a, b in (("kee", rk.kee_C, E1, E2), ("kef", rk.kef_C, E1, F2), ("kff", rk.kff_C, F1, F2)):
+            for k, v in zip(("K", "Ks", "Kl"), fn(a, b, sig, l, zeta, grad=True)):
+                assert rel_err(v, gk["rbf_%s_grad_%s_%s" % (name, k, z)]) <= TOL, (name, k, z)
+    # the pair cut `dK_dD > tol` (rbf_kernel.cpp:395) with a tol that really removes pairs
+    assert rel_err(rk.kff_C(F1, F2, 1.0, 0.2, 2.0, tol=1.0), gk["rbf_kff_tol_l02"]) <= TOL
+    assert rel_err(rk.kef_C(E1, F2, sig, l, 2.0, transpose=True), gk["rbf_kef_z2"].T) <= TOL
+
+
+def test_dot_blocks_vs_golden(gk):
+    from gpr_calculator_b200.kernels import dot_kernel as dk
+    E1, E2, F1, F2 = _inputs(gk)
+    for zeta in (2.0, 3.0):
+        z = "z%d" % int(zeta)
+        assert rel_err(dk.kee_C(E1, E2, 2.0, 1.5, zeta), gk["dot_kee_" + z]) <= TOL
+        assert rel_err(dk.kef_C(E1, F2, 2.0, 1.5, zeta), gk["dot_kef_" + z]) <= TOL
+        assert rel_err(dk.kff_C(F1, F2, 2.0, 1.5, zeta), gk["dot_kff_" + z]) <= TOL
+
+
+def test_kernel_objects_vs_golden(gk):
+    """RBF_mb / Dot_mb assembled matrices incl. the reference quirks (Dot zeta slot, eps diag)."""
+    from gpr_calculator_b200.kernels import RBF_mb, Dot_mb
+    from gpr_calculator_b200.utilities import tuple_to_list
+    E1, E2, F1, F2 = _inputs(gk)
+    sig, l = gk["params"]
+    data, data2 = {"energy": E1, "force": F1}, {"energy": E2, "force": F2}
+    rbf = RBF_mb(para=[sig, l], zeta=2)
+    K = rbf.k_total(data)
+    assert rel_err(K, gk["RBF_k_total"]) <= TOL
+    assert np.abs(K - K.T).max() <= 1e-12 * np.abs(K).max()
+    assert rel_err(rbf.k_total(data2, data, f_tol=1e-12), gk["RBF_k_total_rect"]) <= TOL
+    K, dK = rbf.k_total_with_grad(data)
+    assert rel_err(K, gk["RBF_k_grad_K"]) <= TOL and rel_err(dK, gk["RBF_k_grad_dK"]) <= TOL
+    assert rel_err(rbf.diag({"energy": E1, "force": tuple_to_list(F1)}), gk["RBF_diag"]) <= TOL
+    dot = Dot_mb(para=[2.0, 1.5], zeta=3)
+    assert rel_err(dot.k_total(data), gk["Dot_k_total"]) <= TOL
+    K, dK = dot.k_total_with_grad(data)
+    assert rel_err(K, gk["Dot_k_grad_K"]) <= TOL and rel_err(dK, gk["Dot_k_grad_dK"]) <= TOL
+    assert rel_err(dot.diag({"energy": tuple_to_list(E1, mode="energy"), "force": tuple_to_list(F1)}), gk["Dot_diag"]) <= 1e-9
+    with pytest.raises(ValueError):
+        dot.diag({"force": F1})      # packed tuple rejected like Dot_mb.py:71-78
+
+
+CASES = [
+    # (name, kwargs for make_force side 1, side 2)
+    ("ragged", dict(n_groups=9, lo=3, hi=40), dict(n_groups=7, lo=3, hi=40)),
+    ("single_rows", dict(n_groups=13, lo=1, hi=2), dict(n_groups=5, lo=1, hi=9)),
+    ("large_split_groups", dict(n_groups=3, lo=70, hi=150), dict(n_groups=4, lo=60, hi=100)),
+    ("zero_norm_rows", dict(n_groups=6, lo=4, hi=12, zero_rows=2), dict(n_groups=6, lo=4, hi=12, zero_rows=1)),
+    ("three_species", dict(n_groups=6, lo=5, hi=30, species=(1, 16, 46)), dict(n_groups=5, lo=5, hi=30, species=(1, 16, 46))),
+    ("d24", dict(n_groups=5, lo=5, hi=20, d=24), dict(n_groups=4, lo=5, hi=20, d=24)),
+    ("d7", dict(n_groups=5, lo=5, hi=20, d=7), dict(n_groups=4, lo=5, hi=20, d=7)),
+    ("d32", dict(n_groups=4, lo=5, hi=20, d=32), dict(n_groups=4, lo=5, hi=20, d=32)),
+    ("big_norms", dict(n_groups=5, lo=20, hi=35, scale=7e3), dict(n_groups=5, lo=20, hi=35, scale=7e3)),
+]
+
+
+@pytest.mark.parametrize("name,kw1,kw2", CASES, ids=[c[0] for c in CASES])
+def test_blocks_vs_oracle(oracle_libs, name, kw1, kw2):
+    """Seeded ragged inputs, edge cases of the domain (single-row groups, groups split over CTAs,
+    dropped zero-norm rows, species masks, descriptor lengths) against the CPU oracle."""
+    from gpr_calculator_b200.kernels import rbf_kernel as rk, dot_kernel as dk
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+    d = kw1.get("d", 30)
+    F1, F2 = list_to_tuple(make_force(rng, **kw1)), list_to_tuple(make_force(rng, **kw2))
+    ekw = dict(d=d, species=kw1.get("species", (13, 79)), scale=kw1.get("scale", 1.0))
+    E1 = list_to_tuple(make_energy(rng, 4, **ekw), mode="energy")
+    E2 = list_to_tuple(make_energy(rng, 3, lo=1, hi=130, **ekw), mode="energy")
+    O, OD = oracle_libs.RBFOracle("port"), oracle_libs.DotOracle("port")
+    sig, l = 1.7, 0.6
+    for zeta in (2.0, 3.0, 2.5):
+        for grad in (False, True):
+            for fn_g, fn_o, a, b in ((rk.kff_C, O.kff_C, F1, F2), (rk.kef_C, O.kef_C, E1, F2), (rk.kee_C, O.kee_C, E1, E2)):
+                got, ref = fn_g(a, b, sig, l, zeta, grad=grad), fn_o(a, b, sig, l, zeta, grad=grad)
+                got, ref = (got, ref) if grad else ((got,), (ref,))
+                for x, y in zip(got, ref):
+                    assert x.shape == y.shape and rel_err(x, y) <= TOL, (name, zeta, grad, fn_g.__name__)
+        assert rel_err(dk.kff_C(F1, F2, 2.0, 1.5, zeta), OD.kff_C(F1, F2, 2.0, 1.5, zeta)) <= TOL
+        assert rel_err(dk.kef_C(E1, F2, 2.0, 1.5, zeta), OD.kef_C(E1, F2, 2.0, 1.5, zeta)) <= TOL
+        assert rel_err(dk.kee_C(E1, E2, 2.0, 1.5, zeta), OD.kee_C(E1, E2, 2.0, 1.5, zeta)) <= TOL
+
+
+def test_disjoint_species_give_zero():
+    from gpr_calculator_b200.kernels import rbf_kernel as rk
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(5)
+    F1 = list_to_tuple(make_force(rng, 3, species=(13,)))
+    F2 = list_to_tuple(make_force(rng, 4, species=(79,)))
+    assert np.count_nonzero(rk.kff_C(F1, F2, 1.0, 0.5, 2.0)) == 0
+
+
+def test_descriptor_longer_than_32_fails_loudly():
+    from gpr_calculator_b200 import _lib
+    from gpr_calculator_b200.kernels import rbf_kernel as rk
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(6)
+    F = list_to_tuple(make_force(rng, 2, d=40))
+    with pytest.raises(_lib.GprB200Error):
+        rk.kff_C(F, F, 1.0, 0.5, 2.0)
+
+
+def test_modes_and_windows_agree():
+    """Symmetric build == full build; row windows concatenate to the full matrix; diag mode ==
+    diagonal of the block; K(sigma) = sigma^2 K(1) (size-independent properties)."""
+    from gpr_calculator_b200 import _lib
+    from gpr_calculator_b200.device import Pack, k_total_device, diag_device
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(7)
+    X, dX, ELE, ind = list_to_tuple(make_force(rng, 41, lo=20, hi=36))
+    Xe, Ee, inde = list_to_tuple(make_energy(rng, 9, lo=20, hi=40), mode="energy")
+    f, e = Pack(X, ELE, ind, dxdr=dX), Pack(Xe, Ee, inde)
+    for kern, p1 in ((_lib.RBF, 0.7), (_lib.DOT, 1.1)):
+        grad = kern == _lib.RBF
+        Ks, dKs = k_total_device(kern, 1.3, p1, 2.0, (e, f), None, use_tol=False, grad=grad, symmetric=True)
+        Kf, dKf = k_total_device(kern, 1.3, p1, 2.0, (e, f), None, use_tol=False, grad=grad, symmetric=False)
+        scale = Kf.abs().max().item()
+        assert (Ks - Kf).abs().max().item() <= 1e-13 * scale
+        assert (Ks - Ks.T).abs().max().item() <= 1e-13 * scale
+        if grad:
+            assert (dKs - dKf).abs().max().item() <= 1e-13 * dKf.abs().max().item()
+        rows = []
+        for w in (((0, 4), (0, 13)), ((4, 9), (13, 41))):
+            Kw, _ = k_total_device(kern, 1.3, p1, 2.0, (e, f), None, use_tol=False, grad=False, window=w)
+            rows.append(Kw)
+        NE = 9
+        K2 = torch.cat((rows[0][:4], rows[1][:5], rows[0][4:], rows[1][5:]))
+        assert (K2 - Kf).abs().max().item() <= 1e-13 * scale
+        dg = diag_device(kern, 1.3, p1, 2.0, (None, f), tol=0.0)
+        assert (dg - torch.diagonal(Kf)[NE:]).abs().max().item() <= 1e-13 * scale
+        K1, _ = k_total_device(kern, 1.0, p1, 2.0, (e, f), None, use_tol=False, grad=False)
+        assert (Kf - 1.3 ** 2 * K1).abs().max().item() <= 1e-13 * scale
+
+
+def test_kff_is_psd_and_deterministic():
+    from gpr_calculator_b200 import _lib
+    from gpr_calculator_b200.device import Pack, k_total_device
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(8)
+    X, dX, ELE, ind = list_to_tuple(make_force(rng, 60, lo=25, hi=34))
+    f = Pack(X, ELE, ind, dxdr=dX)
+    K1, _ = k_total_device(_lib.RBF, 1.0, 0.5, 2.0, (None, f), None, use_tol=True, tol=1e-10)
+    K2, _ = k_total_device(_lib.RBF, 1.0, 0.5, 2.0, (None, f), None, use_tol=True, tol=1e-10)
+    assert torch.equal(K1, K2)                              # fixed-order reductions: bitwise reproducible
+    w = torch.linalg.eigvalsh(K1)
+    assert w.min().item() >= -1e-9 * w.max().item()

@@ -1,0 +1,130 @@
+"""CPU: host-side logic of the drop-in (layouts, block assembly, selection, sharding, bookkeeping)."""
+import numpy as np
+import pytest
+
+from helpers import make_force, make_energy
+
+
+def test_list_tuple_roundtrip():
+    from gpr_calculator_b200.utilities import list_to_tuple, tuple_to_list
+    rng = np.random.default_rng(0)
+    fl = make_force(rng, 5, lo=1, hi=6)
+    X, dX, ELE, ind = list_to_tuple(fl)
+    assert X.shape[0] == sum(ind) == dX.shape[0] == len(ELE) and dX.shape[2] == 3
+    back = tuple_to_list((X, dX, ELE, ind))
+    for (x, dx, e), (x2, dx2, e2) in zip(fl, back):
+        assert np.array_equal(x, x2) and np.array_equal(dx, dx2) and np.array_equal(e, e2)
+    el = make_energy(rng, 3)
+    Xe, Ee, inde = list_to_tuple(el, mode="energy")
+    assert [len(x) for x, _ in el] == inde
+    with_vals = list_to_tuple([(x, dx, np.ones(3) * i, e) for i, (x, dx, e) in enumerate(fl)], include_value=True)
+    assert len(with_vals) == 5 and len(with_vals[4]) == 5
+
+
+def test_list_to_tuple_matches_oracle_layout():
+    from gpr_calculator_b200.utilities import list_to_tuple
+    from oracle.kernels import list_to_tuple as olt
+    rng = np.random.default_rng(1)
+    fl = make_force(rng, 4)
+    for a, b in zip(list_to_tuple(fl), olt(fl)):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_build_covariance_dispatch():
+    from gpr_calculator_b200.kernels.base import build_covariance
+    ee, ef, fe, ff = np.ones((2, 2)), 2 * np.ones((2, 6)), 3 * np.ones((6, 2)), 4 * np.ones((6, 6))
+    assert build_covariance(ee, ef, fe, ff).shape == (8, 8)
+    assert build_covariance(None, None, fe, ff).shape == (6, 8)
+    assert build_covariance(ee, ef, None, None).shape == (2, 8)
+    assert build_covariance(None, ef, None, None) is ef
+    assert build_covariance(None, None, None, ff) is ff
+    assert build_covariance(ee, None, fe, None) is None      # not in the reference's table either
+
+
+def test_new_pt():
+    from gpr_calculator_b200.utilities import new_pt
+    x = np.array([1.0, 2.0, 3.0])
+    assert not new_pt((x, 29), [(x * 1.01, 29)])
+    assert new_pt((x, 29), [(x * 1.01, 13)])
+    assert new_pt((x, 29), [(np.array([3.0, -1.0, 0.1]), 29)])
+
+
+def test_split_groups_and_windows():
+    from gpr_calculator_b200.dist import split_groups, row_windows, window_row_ranges
+    rng = np.random.default_rng(2)
+    costs = rng.integers(20, 40, size=101)
+    for parts in (1, 2, 3, 4, 8):
+        b = split_groups(costs, parts)
+        assert b[0] == 0 and b[-1] == len(costs) and all(b[i] <= b[i + 1] for i in range(parts))
+        loads = [costs[b[i]:b[i + 1]].sum() for i in range(parts)]
+        assert max(loads) - min(loads) <= 2 * costs.max()
+    assert split_groups([], 4) == [0, 0, 0, 0, 0]
+    w = row_windows([32] * 5, [30] * 17, 4)
+    rr = window_row_ranges(w, NE=5)
+    covered = sorted(r for pair in rr for r in pair)
+    # energy windows tile [0,5), force windows tile [5, 5+51)
+    assert covered[0][0] == 0 and max(hi for _, hi in covered) == 5 + 3 * 17
+
+
+def _toy_gp():
+    from gpr_calculator_b200.gaussianprocess import GP
+    from gpr_calculator_b200.kernels import RBF_mb
+    return GP(kernel=RBF_mb(para=[1.0, 0.1]), descriptor=None, log_file=None)
+
+
+def test_gp_bookkeeping_without_gpu():
+    rng = np.random.default_rng(3)
+    gp = _toy_gp()
+    fl = make_force(rng, 4, lo=2, hi=5)
+    el = make_energy(rng, 2, lo=3, hi=6)
+    data = {"energy": [(x, 0.5 * i, e) for i, (x, e) in enumerate(el)],
+            "force": [(x, dx, np.full(3, float(i)), e) for i, (x, dx, e) in enumerate(fl)],
+            "db": [("s0", 1.0, None, True, [0, 1]), ("s1", 2.0, None, True, [0, 1])]}
+    gp.set_train_pts(data)
+    assert (gp.N_energy, gp.N_forces, gp.N_queue) == (2, 4, 6)
+    assert gp.y_train.shape == (2 + 12, 1)
+    assert np.array_equal(gp.y_train[:, 0], [0.0, 0.5] + [0.0] * 3 + [1.0] * 3 + [2.0] * 3 + [3.0] * 3)
+    # queue slicing: pretend the first energy and two forces are fitted
+    gp.N_energy_queue, gp.N_forces_queue, gp.N_queue = 1, 2, 3
+    tx = gp.get_train_x()
+    assert len(tx["energy"][-1]) == 1 and len(tx["force"][-1]) == 2
+    assert tx["force"][0].shape[0] == sum(tx["force"][-1])
+    # append mode
+    gp.set_train_pts({"energy": data["energy"][:1], "force": data["force"][:1], "db": [("s2", 0.0, None, True, [0])]}, mode="a+")
+    assert (gp.N_energy, gp.N_forces) == (3, 5) and gp.y_train.shape[0] == 3 + 15
+    assert "RBF" in str(gp) and "3 energy" in str(gp)
+
+
+def test_so3_validation_and_dict():
+    from gpr_calculator_b200.SO3 import SO3
+    s = SO3(nmax=3, lmax=4, rcut=5.0)
+    assert s.ncoefs == 30
+    d = s.save_dict()
+    assert d["_type"] == "SO3" and d["lmax"] == 4
+    t = SO3()
+    t.load_from_dict(d)
+    assert (t.nmax, t.lmax, t.rcut) == (3, 4, 5.0)
+    for bad in (dict(nmax=0), dict(nmax=12), dict(nmax=2.5), dict(lmax=-1), dict(rcut=-1.0), dict(alpha=0), dict(derivative=1)):
+        with pytest.raises(ValueError):
+            SO3(**bad)
+    with pytest.raises(NotImplementedError):
+        SO3(cutoff_function="tanh")
+
+
+def test_kernel_object_surface():
+    from gpr_calculator_b200.kernels import RBF_mb, Dot_mb
+    k = RBF_mb(para=[2.0, 0.5], zeta=2)
+    assert str(k) == "2.00000**2 *RBF(0.50000)" and k.parameters() == [2.0, 0.5] and k.name == "RBF"
+    k2 = RBF_mb()
+    k2.load_from_dict(k.save_dict())
+    assert k2.parameters() == [2.0, 0.5] and k2.bounds == [[1e-2, 5e+1], [1e-1, 1e+1]]
+    d = Dot_mb(para=[2, 2.0], zeta=3)
+    assert str(d) == "2.000**2 *Dot(2.000)" and d.save_dict()["sigma0"] == 2.0
+
+
+def test_cur_selects_null_space_rows():
+    from gpr_calculator_b200.gaussianprocess import CUR
+    v = np.array([1.0, 1.0, 0.0])
+    K = np.outer(v, v) + np.diag([0.0, 0.0, 1.0])     # rows 0 and 1 are redundant
+    ids = CUR(K, 1e-10)
+    assert len(ids) == 1 and ids[0] in (0, 1)

@@ -1,0 +1,167 @@
+"""CPU: the oracle (C port, compiled reference when present, numpy layers) against the golden
+vectors produced by the reference itself (tests/golden/gen_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import rel_err
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-11   # oracle vs reference: same algorithm, different summation order
+
+
+@pytest.fixture(scope="module")
+def gk():
+    return np.load(os.path.join(GOLD, "kernels.npz"))
+
+
+def _inputs(g):
+    F1 = (g["F1_x"], g["F1_dxdr"], g["F1_ele"], list(g["F1_ind"]))
+    F2 = (g["F2_x"], g["F2_dxdr"], g["F2_ele"], list(g["F2_ind"]))
+    E1 = (g["E1_x"], g["E1_ele"], list(g["E1_ind"]))
+    E2 = (g["E2_x"], g["E2_ele"], list(g["E2_ind"]))
+    return E1, E2, F1, F2
+
+
+def _backends(ok):
+    return ["port", "ref"] if ok.have_ref() else ["port"]
+
+
+def test_rbf_blocks_match_golden(oracle_libs, gk):
+    ok = oracle_libs
+    E1, E2, F1, F2 = _inputs(gk)
+    sig, l = gk["params"]
+    for be in _backends(ok):
+        O = ok.RBFOracle(be)
+        tol = 0 if be == "ref" else TOL
+        for zeta in (2.0, 3.0):
+            z = "z%d" % int(zeta)
+            assert rel_err(O.kee_C(E1, E2, sig, l, zeta), gk["rbf_kee_" + z]) <= tol
+            assert rel_err(O.kef_C(E1, F2, sig, l, zeta), gk["rbf_kef_" + z]) <= tol
+            assert rel_err(O.kff_C(F1, F2, sig, l, zeta, tol=1e-12), gk["rbf_kff_" + z]) <= tol
+            for name, fn, a, b in (("kee", O.kee_C, E1, E2), ("kef", O.kef_C, E1, F2), ("kff", O.kff_C, F1, F2)):
+                got = fn(a, b, sig, l, zeta, grad=True)
+                for k, v in zip(("K", "Ks", "Kl"), got):
+                    assert rel_err(v, gk["rbf_%s_grad_%s_%s" % (name, k, z)]) <= tol, (be, name, k, z)
+        assert rel_err(O.kff_C(F1, F2, 1.0, 0.2, 2.0, tol=1.0), gk["rbf_kff_tol_l02"]) <= tol
+
+
+def test_tol_cut_removes_pairs(oracle_libs, gk):
+    """The golden tol case must differ from the uncut kernel, otherwise it pins nothing."""
+    _, _, F1, F2 = _inputs(gk)
+    O = oracle_libs.RBFOracle("port")
+    uncut = O.kff_C(F1, F2, 1.0, 0.2, 2.0, tol=0.0)
+    assert rel_err(uncut, gk["rbf_kff_tol_l02"]) > 1e-6
+
+
+def test_dot_blocks_match_golden(oracle_libs, gk):
+    ok = oracle_libs
+    E1, E2, F1, F2 = _inputs(gk)
+    for be in _backends(ok):
+        O = ok.DotOracle(be)
+        tol = 0 if be == "ref" else TOL
+        for zeta in (2.0, 3.0):
+            z = "z%d" % int(zeta)
+            assert rel_err(O.kee_C(E1, E2, 2.0, 1.5, zeta), gk["dot_kee_" + z]) <= tol
+            assert rel_err(O.kef_C(E1, F2, 2.0, 1.5, zeta), gk["dot_kef_" + z]) <= tol
+            assert rel_err(O.kff_C(F1, F2, 2.0, 1.5, zeta), gk["dot_kff_" + z]) <= tol
+
+
+def test_kernel_objects_match_golden(oracle_libs, gk):
+    from oracle import gp as ogp
+    E1, E2, F1, F2 = _inputs(gk)
+    sig, l = gk["params"]
+    data, data2 = {"energy": E1, "force": F1}, {"energy": E2, "force": F2}
+    rbf = ogp.RBFKernelOracle([sig, l], zeta=2)
+    assert rel_err(rbf.k_total(data), gk["RBF_k_total"]) <= TOL
+    assert rel_err(rbf.k_total(data2, data, f_tol=1e-12), gk["RBF_k_total_rect"]) <= TOL
+    K, dK = rbf.k_total_with_grad(data)
+    assert rel_err(K, gk["RBF_k_grad_K"]) <= TOL and rel_err(dK, gk["RBF_k_grad_dK"]) <= TOL
+    assert rel_err(rbf.diag(data), gk["RBF_diag"]) <= TOL
+    dot = ogp.DotKernelOracle([2.0, 1.5], zeta=3)
+    assert rel_err(dot.k_total(data), gk["Dot_k_total"]) <= TOL
+    K, dK = dot.k_total_with_grad(data)
+    assert rel_err(K, gk["Dot_k_grad_K"]) <= TOL and rel_err(dK, gk["Dot_k_grad_dK"]) <= TOL
+
+
+def test_so3_oracle_matches_golden():
+    from oracle import so3 as oso3
+    g = np.load(os.path.join(GOLD, "so3.npz"))
+    for k in range(3):
+        prm = g["s%d_prm" % k]
+        x, dxdr, seq = oso3.so3_calculate(g["s%d_pos" % k], g["s%d_cell" % k], g["s%d_pbc" % k], g["s%d_numbers" % k],
+                                          int(prm[0]), int(prm[1]), float(prm[2]), float(prm[3]))
+        assert np.array_equal(seq, g["s%d_seq" % k])          # bit-exact indexing
+        assert rel_err(x, g["s%d_x" % k]) <= 1e-11
+        assert rel_err(dxdr, g["s%d_dxdr" % k]) <= 1e-11
+
+
+def std_tolerance(K, noise_e, noise_f, NE, diag):
+    """Absolute tolerance on a predictive VARIANCE: max(1e-8^2-equivalent, 50 eps cond(K) max(diag))."""
+    Kn = K.copy()
+    idx = np.arange(len(K))
+    Kn[idx[:NE], idx[:NE]] += noise_e ** 2
+    Kn[idx[NE:], idx[NE:]] += noise_f ** 2
+    cond = np.linalg.cond(Kn)
+    return max(1e-16, 50 * np.finfo(float).eps * cond * float(np.max(diag)))
+
+
+def _gp_training(g):
+    """Rebuild the golden GP training dict with the oracle descriptor."""
+    from oracle import so3 as oso3
+    from oracle.ref_harness import Atoms
+    des = oso3.SO3Oracle(3, 4, 5.0, 2.0)
+    energy, force = [], []
+    for k in range(3):
+        at = Atoms(g["numbers"], g["t%d_pos" % k], g["cell"], g["pbc"])
+        d = des.calculate(at)
+        ele = np.asarray(at.numbers)
+        energy.append((d["x"], float(g["t%d_E" % k]) / len(at), ele))
+        for i in range(len(at)):
+            ids = np.argwhere(d["seq"][:, 1] == i).flatten()
+            c = d["seq"][ids, 0]
+            force.append((d["x"][c], d["dxdr"][ids], g["t%d_F" % k][i], ele[c]))
+    return des, energy, force
+
+
+def test_gp_oracle_matches_golden(oracle_libs):
+    from oracle import gp as ogp
+    from oracle.kernels import list_to_tuple
+    from oracle.ref_harness import Atoms
+    g = np.load(os.path.join(GOLD, "gp.npz"))
+    des, energy, force = _gp_training(g)
+    Xe = list_to_tuple(energy, include_value=True, mode="energy")
+    Xf = list_to_tuple(force, include_value=True)
+    train_x = {"energy": Xe[:3], "force": Xf[:4]}
+    y = np.concatenate((np.array(Xe[3]), np.array(Xf[4]).reshape(-1))).reshape(-1, 1)
+    assert np.allclose(y, g["y_train"], rtol=0, atol=1e-14)
+    for tag, prm in (("a", [1.0, 0.1]), ("b", [2.0, 0.8])):
+        ker = ogp.RBFKernelOracle(prm, zeta=2.0)
+        lml, grad = ogp.log_marginal_likelihood(ker, train_x, y, 0.002, 0.1)
+        assert abs(lml - g["lml_" + tag]) <= 1e-8 * abs(g["lml_" + tag])
+        assert rel_err(grad, g["lml_grad_" + tag]) <= 1e-7
+    ker = ogp.RBFKernelOracle([2.0, 0.8], zeta=2.0)
+    assert rel_err(ker.k_total(train_x), g["K_b"]) <= 1e-11
+    L, alpha, Kinv = ogp.fit_factors(ker, train_x, y, 0.002, 0.1)
+    assert rel_err(alpha, g["alpha_b"]) <= 1e-7
+    # predict the held-out structure (free atoms only, as predict_structure does)
+    at = Atoms(g["numbers"], g["test_pos"], g["cell"], g["pbc"])
+    d = des.calculate(at)
+    ele = np.asarray(at.numbers)
+    free = [i for i in range(len(at)) if i not in set(g["fixed"])]
+    fdata = []
+    for i in free:
+        ids = np.argwhere(d["seq"][:, 1] == i).flatten()
+        c = d["seq"][ids, 0]
+        fdata.append((d["x"][c], d["dxdr"][ids], ele[c]))
+    X = {"energy": list_to_tuple([(d["x"], ele)], mode="energy"), "force": fdata}
+    mean, std = ogp.predict_rows(ker, X, train_x, alpha, Kinv, f_tol=1e-12, return_std=True)
+    assert abs(mean[0] * len(at) - g["pred_E"]) <= 1e-8
+    assert np.abs(mean[1:].reshape(-1, 3) - g["pred_F"][free]).max() <= 1e-8
+    # sigma: var = diag - K* K^-1 K*^T is a cancellation amplified by cond(K) (noise^2 = 4e-6 against
+    # eigenvalues ~ N sigma^2); two correct fp64 evaluations agree to ~ eps * cond(K) * diag, not to 1e-8
+    # (SURVEY.md §7.3).  Where that bound is below 1e-8 the plain 1e-8 tolerance is what is enforced.
+    bound = std_tolerance(g["K_b"], 0.002, 0.1, 3, ker.diag(X))
+    assert abs(std[0] ** 2 - g["pred_E_std"] ** 2) <= bound
+    assert np.abs(std[1:].reshape(-1, 3) ** 2 - g["pred_F_std"][free] ** 2).max() <= bound
