@@ -12,7 +12,7 @@ c_int, c_ll, c_dbl, c_vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, cty
 c_int_p = ctypes.POINTER(ctypes.c_int)
 
 RBF, DOT = 0, 1
-FF_FULL, FF_SYMMETRIC, FF_DIAG = 0, 1, 2
+FF_FULL, FF_SYMMETRIC, FF_DIAG, FF_UPPER = 0, 1, 2, 3
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_LINALG = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); every symbol declared in include/gpr_b200.h
@@ -35,7 +35,9 @@ SIGNATURES = {
     "gprb_chol_solve_vec": (c_int, [c_vp, c_ll, c_int, c_vp, c_vp]),
     "gprb_chol_inverse": (c_int, [c_vp, c_ll, c_int, c_vp, c_ll, c_vp]),
     "gprb_lml_terms": (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp]),
-    "gprb_lml_grad_trace": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_ll, c_vp, c_ll, c_int, c_dbl, c_dbl, c_vp, c_vp]),
+    "gprb_lml_grad_trace": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_ll, c_vp, c_ll, c_int, c_dbl, c_dbl, c_int, c_vp, c_vp]),
+    "gprb_symmetrize": (c_int, [c_vp, c_ll, c_int, c_vp]),
+    "gprb_fp64_dmma_peak": (c_int, [c_vp, c_vp]),
     "gprb_w_block_sum": (c_int, [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "gprb_predict": (c_int, [c_int, c_int, c_vp, c_ll, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gprb_so3_neighbors": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
         const int G = P.n_groupsB;
         int ga = (int)((long long)G * blockIdx.y / P.n_splits);
         int gb = (int)((long long)G * (blockIdx.y + 1) / P.n_splits);
-        if (P.mode == GPRB_FF_SYMMETRIC) ga = max(ga, g0);
+        if (P.mode == GPRB_FF_SYMMETRIC || P.mode == GPRB_FF_UPPER) ga = max(ga, g0);
         if (P.mode == GPRB_FF_DIAG) { ga = max(ga, g0); gb = min(gb, g1); }
         if (gb < ga) gb = ga;
         c_begin = P.gcpB[ga];
@@ -397,12 +397,12 @@ extern "C" int gprb_kff(int kernel, const gprb_pack *f1_, const gprb_pack *f2, d
     GPRB_REQUIRE(f1->ncols == 3 && f2->ncols == 3, "gprb_kff: both sides must be force packs");
     GPRB_REQUIRE(f1->d == f2->d, "gprb_kff: descriptor length mismatch %d vs %d", f1->d, f2->d);
     GPRB_REQUIRE(kernel == GPRB_KERNEL_RBF || kernel == GPRB_KERNEL_DOT, "gprb_kff: unknown kernel %d", kernel);
-    GPRB_REQUIRE(mode >= 0 && mode <= 2, "gprb_kff: unknown mode %d", mode);
+    GPRB_REQUIRE(mode >= 0 && mode <= 3, "gprb_kff: unknown mode %d", mode);
     GPRB_REQUIRE(0 <= grp_begin && grp_begin <= grp_end && grp_end <= f1->n_groups, "gprb_kff: bad window [%d,%d)", grp_begin, grp_end);
     GPRB_REQUIRE(!(dK && kernel == GPRB_KERNEL_DOT), "gprb_kff: Dot has no dK output (closed form, see header)");
     if (mode == GPRB_FF_SYMMETRIC)
         GPRB_REQUIRE(f1 == f2 && grp_begin == 0 && grp_end == f1->n_groups, "gprb_kff: symmetric mode needs f1 == f2 and the full window");
-    if (mode == GPRB_FF_DIAG) GPRB_REQUIRE(f1 == f2, "gprb_kff: diag mode needs f1 == f2");
+    if (mode == GPRB_FF_DIAG || mode == GPRB_FF_UPPER) GPRB_REQUIRE(f1 == f2, "gprb_kff: diag / upper mode needs f1 == f2");
     if (f1->ks > GPRB_MAX_KS) {
         gprb_set_error("gprb_kff: descriptor length %d > 32 is not supported by the DMMA kernels yet", f1->d);
         return GPRB_ERR_UNSUPPORTED;

@@ -37,6 +37,18 @@ __global__ void add_noise_kernel(double *K, long long ld, int N, int NE, double 
     if (i < N) K[(long long)i * ld + i] += (i < NE) ? ne2 : nf2;
 }
 
+// A[i][j] = A[j][i] for i > j (fill the lower triangle from the upper one)
+__global__ void mirror_upper_kernel(double *A, long long ld, int N) {
+    __shared__ double t[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;       // source block (bi, bj) with bj >= bi
+    if (bj < bi) return;
+    const int i = bi * 32 + threadIdx.y, j = bj * 32 + threadIdx.x;
+    if (i < N && j < N) t[threadIdx.y][threadIdx.x] = A[(long long)i * ld + j];
+    __syncthreads();
+    const int ti = bj * 32 + threadIdx.y, tj = bi * 32 + threadIdx.x;   // destination (transposed block)
+    if (ti < N && tj < N && ti > tj) A[(long long)ti * ld + tj] = t[threadIdx.x][threadIdx.y];
+}
+
 // after potri on the (row-major) lower triangle: copy it to the upper triangle
 __global__ void mirror_lower_kernel(double *A, long long ld, int N) {
     __shared__ double t[32][33];
@@ -78,7 +90,7 @@ __global__ void lml_terms_kernel(const double *L, long long ld, int N, const dou
 __global__ void __launch_bounds__(256) trace_kernel(int N, int r0, int r1, const double *__restrict__ alpha,
                                                     const double *__restrict__ Kinv, long long ldi,
                                                     const double *__restrict__ dK, long long lddk,
-                                                    int NE, double we, double wf, double *partial) {
+                                                    int NE, double we, double wf, int upper_only, double *partial) {
     __shared__ double sh[32];
     double acc = 0.0, acc2 = 0.0;
     for (int i = r0 + blockIdx.x; i < r1; i += gridDim.x) {
@@ -86,7 +98,14 @@ __global__ void __launch_bounds__(256) trace_kernel(int N, int r0, int r1, const
         const double *ki = Kinv + (long long)i * ldi;
         if (dK) {
             const double *di = dK + (long long)(i - r0) * lddk;
-            for (int j = threadIdx.x; j < N; j += blockDim.x) acc = fma(fma(ai, alpha[j], -ki[j]), di[j], acc);
+            if (upper_only) {
+                for (int j = i + threadIdx.x; j < N; j += blockDim.x) {
+                    const double t = fma(ai, alpha[j], -ki[j]) * di[j];
+                    acc += (j == i) ? t : 2.0 * t;
+                }
+            } else {
+                for (int j = threadIdx.x; j < N; j += blockDim.x) acc = fma(fma(ai, alpha[j], -ki[j]), di[j], acc);
+            }
         }
         if (threadIdx.x == 0) acc2 += (ai * ai - ki[i]) * (i < NE ? we : wf);
     }
@@ -229,7 +248,7 @@ extern "C" int gprb_lml_terms(const double *L, long long ldl, int N, const doubl
 
 extern "C" int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha, const double *Kinv, long long ldi,
                                    const double *dK_rows, long long lddk, int NE, double we, double wf,
-                                   double *out_host, void *stream) {
+                                   int upper_only, double *out_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(alpha && Kinv && out_host && 0 <= r0 && r0 <= r1 && r1 <= N, "gprb_lml_grad_trace: bad argument");
     out_host[0] = out_host[1] = 0.0;
@@ -237,7 +256,7 @@ extern "C" int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha, c
     const int blocks = (r1 - r0) < 1184 ? (r1 - r0) : 1184;   // 8 x 148
     double *d = nullptr;
     GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
-    trace_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, alpha, Kinv, ldi, dK_rows, lddk, NE, we, wf, d);
+    trace_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, alpha, Kinv, ldi, dK_rows, lddk, NE, we, wf, upper_only, d);
     GPRB_CUDA(cudaGetLastError());
     final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, d + 2 * blocks);
     GPRB_CUDA(cudaGetLastError());
@@ -285,5 +304,61 @@ extern "C" int gprb_predict(int m, int N, const double *Ks, long long ldks, cons
     }
     predict_rows_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, var ? work : nullptr, diag, mean, var);
     GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+extern "C" int gprb_symmetrize(double *A, long long ld, int n, void *stream) {
+    GPRB_REQUIRE(A && n >= 0, "gprb_symmetrize: bad argument");
+    if (n == 0) return GPRB_OK;
+    dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 32);
+    mirror_upper_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, ld, n);
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+namespace {
+__global__ void dmma_peak_kernel(double *out, int iters) {
+    double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int gprb_fp64_dmma_peak(double *tflops_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(tflops_host, "gprb_fp64_dmma_peak: NULL output");
+    int dev = 0, sms = 0;
+    GPRB_CUDA(cudaGetDevice(&dev));
+    GPRB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *d = nullptr;
+    GPRB_CUDA(cudaMalloc((void **)&d, 1024 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    GPRB_CUDA(cudaEventCreate(&e0));
+    GPRB_CUDA(cudaEventCreate(&e1));
+    const int iters = 20000, warps = 8;
+    dmma_peak_kernel<<<sms, warps * 32, 0, st>>>(d, iters / 10);
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        GPRB_CUDA(cudaEventRecord(e0, st));
+        dmma_peak_kernel<<<sms, warps * 32, 0, st>>>(d, iters);
+        GPRB_CUDA(cudaEventRecord(e1, st));
+        GPRB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        GPRB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops_host = (double)sms * warps * iters * 16.0 * 512.0 / (best * 1e-3) * 1e-12;
     return GPRB_OK;
 }

@@ -252,11 +252,11 @@ class GP():
                 if is_rbf:
                     dptr = c_vp(dK.data_ptr() + off * dK.shape[1] * 8)
                 _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, dptr, N, NE,
-                          float(noise_e) ** 2, float(noise_f) ** 2, out, st)
+                          float(noise_e) ** 2, float(noise_f) ** 2, 0, out, st)
                 g_l += out[0]
                 half_w_noise += out[1]
                 _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, c_vp(0), N, NE,
-                          2.0 * float(noise_e), 2.0 * float(noise_f), out, st)
+                          2.0 * float(noise_e), 2.0 * float(noise_f), 0, out, st)
                 half_w_base += out[1]
             off += r1 - r0
         g_s0 = 0.0

@@ -37,7 +37,9 @@ enum { GPRB_KERNEL_RBF = 0, GPRB_KERNEL_DOT = 1 };
 /* mode of the force-force builder */
 enum { GPRB_FF_FULL = 0,      /* every (I,J) block of the window                                  */
        GPRB_FF_SYMMETRIC = 1, /* side1 is side2: evaluate J >= I only and mirror the block         */
-       GPRB_FF_DIAG = 2 };    /* only the diagonal entries of the (I,I) blocks -> vector [3*G]     */
+       GPRB_FF_DIAG = 2,      /* only the diagonal entries of the (I,I) blocks -> vector [3*G]     */
+       GPRB_FF_UPPER = 3 };   /* side1 is side2, any window: evaluate J >= I only, no mirroring; the
+                                 blocks left of the diagonal are NOT written (see gprb_symmetrize)   */
 
 int gprb_version(void);
 const char *gprb_last_error(void);   /* thread-local message of the last failing call */
@@ -111,16 +113,24 @@ int gprb_chol_solve_vec(const double *L_dev, long long ldl, int N, double *b_dev
 /* Kinv = (L L^T)^-1, full symmetric matrix, out of place (cuSOLVER potri + mirror)
  * (gaussianprocess.py:128-131, 195). */
 int gprb_chol_inverse(const double *L_dev, long long ldl, int N, double *Kinv_dev, long long ldi, void *stream);
+/* A[i][j] = A[j][i] for all i > j of the n x n block at A (fills the lower triangle from the upper
+ * one after an all-gather of GPRB_FF_UPPER row blocks). */
+int gprb_symmetrize(double *A_dev, long long ld, int n, void *stream);
 /* out_host[0] = sum_i log L_ii ; out_host[1] = y.alpha                 (gaussianprocess.py:183-186) */
 int gprb_lml_terms(const double *L_dev, long long ldl, int N, const double *y_dev, const double *alpha_dev,
                    double *out_host, void *stream);
 /* out_host[0] = 1/2 sum_{i in [r0,r1), j} (alpha_i alpha_j - Kinv_ij) dK_ij  with dK given for
  * rows [r0,r1) only (row-block sharded; all-reduce the scalar across ranks).
  * out_host[1] = 1/2 sum_i (alpha_i^2 - Kinv_ii) * w_i, w_i = (i<NE ? we : wf) over the same rows
- * (noise / sigma terms).                                           (gaussianprocess.py:188-198) */
+ * (noise / sigma terms).                                           (gaussianprocess.py:188-198)
+ * upper_only != 0: dK holds valid entries only for columns j >= i (GPRB_FF_UPPER build); the sum
+ * then runs over j >= i with weight 2 off the diagonal (W and dK are symmetric). */
 int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha_dev, const double *Kinv_dev, long long ldi,
                         const double *dK_rows_dev, long long lddk, int NE, double we, double wf,
-                        double *out_host, void *stream);
+                        int upper_only, double *out_host, void *stream);
+/* Live FP64 tensor-pipe roofline denominator: DMMA.8x8x4 issue-rate micro-benchmark (all SMs,
+ * 16 independent accumulators per warp).  MEASURED_PEAKS.json carries no fp64 entry. */
+int gprb_fp64_dmma_peak(double *tflops_host, void *stream);
 /* 1/2 sum over the block [r0,r1) x [c0,c1) of (alpha_i alpha_j - Kinv_ij)   (Dot d/dsigma0 term) */
 int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const double *alpha_dev, const double *Kinv_dev,
                      long long ldi, double *out_host, void *stream);
