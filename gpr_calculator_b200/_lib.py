@@ -19,6 +19,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_LINALG = 0, 1, 2, 3, 4
 SIGNATURES = {
     "gprb_version": (c_int, []),
     "gprb_last_error": (ctypes.c_char_p, []),
+    "gprb_launch_count": (c_ll, []),
     "gprb_device_info": (c_int, [c_int_p, c_int_p, c_int_p]),
     "gprb_pack_create": (c_int, [ctypes.POINTER(c_vp), c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_dbl, c_vp]),
     "gprb_pack_destroy": (None, [c_vp]),
@@ -85,5 +86,18 @@ def check(code):
         raise GprB200Error(code, msg)
 
 
+# Optional per-call device timing (bench.py): set PROFILE to a list and every call() appends
+# (name, start_event, end_event), CUDA events recorded on the current torch stream around the call.
+PROFILE = None
+
+
 def call(name, *args):
+    if PROFILE is None:
+        check(getattr(load(), name)(*args))
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(load(), name)(*args))
+    e1.record()
+    PROFILE.append((name, e0, e1))

@@ -13,6 +13,11 @@
 
 void gprb_set_error(const char *fmt, ...);
 
+// kernels launched by this library so far (gprb_launch_count); bumped next to every <<< >>>
+#include <atomic>
+extern std::atomic<long long> g_gprb_launches;
+#define GPRB_LAUNCHED() (g_gprb_launches.fetch_add(1, std::memory_order_relaxed))
+
 #define GPRB_CUDA(call)                                                                         \
     do {                                                                                        \
         cudaError_t _e = (call);                                                                \

@@ -175,6 +175,7 @@ extern "C" int gprb_kee(int kernel, const gprb_pack *e1, const gprb_pack *e2, do
     const size_t smem = (size_t)EE_MAX_SROWS * 4 * P.ks * sizeof(double);
     GPRB_REQUIRE(smem <= 48 * 1024, "gprb_kee: descriptor length %d too large for the staging buffer", e1->d);
     kee_kernel<<<dim3(nI, gy), 256, smem, st>>>(P);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }
@@ -190,6 +191,7 @@ extern "C" int gprb_kee_diag(int kernel, const gprb_pack *e, double p0, double p
     P.PA = e->P; P.eleA = e->elep; P.tile_ptrA = e->d_tile_ptr; P.rowsA = e->d_group_rows; P.ks = e->ks;
     P.K = out;
     kee_diag_kernel<<<e->n_groups, 128, 0, st>>>(P, e->norm, GPRB_EPS_NORM);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }

@@ -348,6 +348,7 @@ int launch_cov(const CovParams &P, int n_blocks, cudaStream_t st) {
     }
     dim3 grid(n_blocks, P.n_splits);
     kern<<<grid, THREADS, smem, st>>>(P);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }

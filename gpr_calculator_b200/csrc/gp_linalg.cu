@@ -169,6 +169,7 @@ extern "C" int gprb_add_noise(double *K, long long ldk, int N, int NE, double no
     GPRB_REQUIRE(K && N >= 0, "gprb_add_noise: bad argument");
     if (N == 0) return GPRB_OK;
     add_noise_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(K, ldk, N, NE, noise_e * noise_e, noise_f * noise_f);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }
@@ -229,6 +230,7 @@ extern "C" int gprb_chol_inverse(const double *L, long long ldl, int N, double *
     if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotri status %d", (int)cs); return GPRB_ERR_CUDA; }
     dim3 grid((N + 31) / 32, (N + 31) / 32), block(32, 32);
     mirror_lower_kernel<<<grid, block, 0, st>>>(Kinv, ldi, N);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }
@@ -240,6 +242,7 @@ extern "C" int gprb_lml_terms(const double *L, long long ldl, int N, const doubl
     double *d = nullptr;
     GPRB_CUDA(cudaMallocAsync((void **)&d, 2 * sizeof(double), st));
     lml_terms_kernel<<<1, 1024, 0, st>>>(L, ldl, N, y, alpha, d);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     int rc = copy_scalars(out_host, d, 2, st);
     cudaFreeAsync(d, st);
@@ -257,8 +260,10 @@ extern "C" int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha, c
     double *d = nullptr;
     GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
     trace_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, alpha, Kinv, ldi, dK_rows, lddk, NE, we, wf, upper_only, d);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, d + 2 * blocks);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     int rc = copy_scalars(out_host, d + 2 * blocks, 2, st);
     cudaFreeAsync(d, st);
@@ -276,8 +281,10 @@ extern "C" int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const dou
     double *d = nullptr;
     GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
     block_sum_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, c0, c1, alpha, Kinv, ldi, d);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, d + 2 * blocks);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     double tmp[2];
     int rc = copy_scalars(tmp, d + 2 * blocks, 2, st);
@@ -303,6 +310,7 @@ extern "C" int gprb_predict(int m, int N, const double *Ks, long long ldks, cons
         if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDgemm status %d", (int)bs); return GPRB_ERR_CUDA; }
     }
     predict_rows_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, var ? work : nullptr, diag, mean, var);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }
@@ -312,6 +320,7 @@ extern "C" int gprb_symmetrize(double *A, long long ld, int n, void *stream) {
     if (n == 0) return GPRB_OK;
     dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 32);
     mirror_upper_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, ld, n);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }

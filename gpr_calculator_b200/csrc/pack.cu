@@ -21,6 +21,9 @@ void gprb_set_error(const char *fmt, ...) {
 extern "C" const char *gprb_last_error(void) { return g_err.c_str(); }
 extern "C" int gprb_version(void) { return 100; }
 
+std::atomic<long long> g_gprb_launches{0};
+extern "C" long long gprb_launch_count(void) { return g_gprb_launches.load(); }
+
 extern "C" int gprb_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     int dev = 0;
     GPRB_CUDA(cudaGetDevice(&dev));
@@ -191,6 +194,7 @@ extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_
         const int blocks = (n_padded + wpb - 1) / wpb;
         prep_rows_kernel<<<blocks, threads, 0, st>>>(n_padded, d, ncols, p->ks, norm_eps, dx, ddx, de, d_src,
                                                      p->P, p->norm, p->elep);
+        GPRB_LAUNCHED();
         PK_CUDA(cudaGetLastError());
     }
     if (ox) PK_CUDA(cudaFreeAsync(ox, st));

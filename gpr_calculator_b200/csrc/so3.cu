@@ -410,6 +410,7 @@ extern "C" int gprb_so3_neighbors(int n_struct, int n_atoms, const int *atom_ptr
     SO3Geom g{atom_ptr, struct_of, pos, cell, nimg, rcut};
     const int wpb = 4;
     so3_neighbors_kernel<<<(n_atoms + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(g, n_atoms, mode, nnb, nuniq, nb_ptr, nb_j, nb_rvec);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }
@@ -423,6 +424,7 @@ extern "C" int gprb_so3_radial(int n_nb, const double *nb_rvec, int nmax, int lm
     const int wpb = 4;
     const size_t smem = (size_t)wpb * 2 * nmax * (lmax + 1) * sizeof(double);
     so3_radial_kernel<<<(n_nb + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(n_nb, nb_rvec, p, rad);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }
@@ -447,6 +449,7 @@ extern "C" int gprb_so3_power(int n_atoms, const int *nb_ptr, const int *nb_j, c
         configured = smem;
     }
     so3_power_kernel<<<n_atoms, 128, smem, (cudaStream_t)stream>>>(a, p);
+    GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }

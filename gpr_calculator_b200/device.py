@@ -179,6 +179,78 @@ def packs_of(data):
 # ------------------------------------------------------------------------------------------------
 # covariance assembly  [[K_ee, K_ef], [K_fe, K_ff]]  (kernels/base.py:3-30 build_covariance)
 # ------------------------------------------------------------------------------------------------
+def _sizes(side):
+    e, f = side
+    return (e.n_groups if e is not None else 0), (f.n_groups if f is not None else 0)
+
+
+def _at(t, r, c):
+    """Pointer to element (r, c) of a row-major 2-D tensor view (or NULL)."""
+    return c_vp(0) if t is None else c_vp(t.data_ptr() + (r * t.stride(0) + c) * t.element_size())
+
+
+def build_energy_rows(kernel, p0, p1, zeta, side1, side2, window, K, dK=None, zeta_ef=None, kfe_rows=None):
+    """Rows of side-1 energy groups [ea, eb): K[:, :NE2] = K_ee, K[:, NE2:] = K_ef.
+
+    K / dK: [eb - ea, NE2 + 3 NF2] row-major views (a row stride > n_cols is fine).  When `kfe_rows`
+    = (Kfe, dKfe) is given (training matrix, full window) the transposed block K_fe is written in
+    the same pass ([3 NF, >= NE] views)."""
+    e1, _ = side1
+    e2, f2 = side2
+    NE2, NF2 = _sizes(side2)
+    ea, eb = window
+    if e1 is None or eb <= ea:
+        return
+    zeta_ef = zeta if zeta_ef is None else zeta_ef
+    st = stream()
+    ld = K.stride(0)
+    ldd = dK.stride(0) if dK is not None else 0
+    if e2 is not None:
+        _lib.call("gprb_kee", kernel, e1.handle, e2.handle, p0, p1, float(zeta), ea, eb, _at(K, 0, 0), ld, _at(dK, 0, 0), ldd, st)
+    if f2 is None:
+        return
+    Kfe, dKfe = kfe_rows if kfe_rows is not None else (None, None)
+    if (ea, eb) == (0, e1.n_groups):
+        _lib.call("gprb_kef", kernel, e1.handle, f2.handle, p0, p1, float(zeta_ef), 0, NF2,
+                  _at(K, 0, NE2), ld, _at(Kfe, 0, 0), Kfe.stride(0) if Kfe is not None else 0,
+                  _at(dK, 0, NE2), ldd, _at(dKfe, 0, 0), dKfe.stride(0) if dKfe is not None else 0, st)
+    else:
+        # the K_ef kernel windows over force groups: build the full-height block, keep my rows
+        tmp = torch.empty((e1.n_groups, 3 * NF2), dtype=F64, device="cuda")
+        dtmp = torch.empty((e1.n_groups, 3 * NF2), dtype=F64, device="cuda") if dK is not None else None
+        _lib.call("gprb_kef", kernel, e1.handle, f2.handle, p0, p1, float(zeta_ef), 0, NF2,
+                  ptr(tmp), 3 * NF2, c_vp(0), 0, ptr(dtmp), 3 * NF2, c_vp(0), 0, st)
+        K[:, NE2:NE2 + 3 * NF2] = tmp[ea:eb]
+        if dK is not None:
+            dK[:, NE2:NE2 + 3 * NF2] = dtmp[ea:eb]
+
+
+def build_force_rows(kernel, p0, p1, zeta, side1, side2, window, K, dK=None, use_tol=True, tol=1e-10,
+                     zeta_ef=None, zeta_ff=None, ff_mode=_lib.FF_FULL, skip_kfe=False):
+    """Rows of side-1 force groups [fa, fb): K[:, :NE2] = K_fe, K[:, NE2:] = K_ff.
+
+    K / dK: [3 (fb - fa), NE2 + 3 NF2] row-major views.  ff_mode: FF_FULL, FF_SYMMETRIC (side1 is
+    side2, full window, mirrored entries written) or FF_UPPER (side1 is side2: only blocks J >= I
+    are written; finish with gprb_symmetrize)."""
+    _, f1 = side1
+    e2, f2 = side2
+    NE2, NF2 = _sizes(side2)
+    fa, fb = window
+    if f1 is None or fb <= fa:
+        return
+    zeta_ef = zeta if zeta_ef is None else zeta_ef
+    zeta_ff = zeta if zeta_ff is None else zeta_ff
+    st = stream()
+    ld = K.stride(0)
+    ldd = dK.stride(0) if dK is not None else 0
+    if e2 is not None and not skip_kfe:
+        _lib.call("gprb_kef", kernel, e2.handle, f1.handle, p0, p1, float(zeta_ef), fa, fb,
+                  c_vp(0), 0, _at(K, 0, 0), ld, c_vp(0), 0, _at(dK, 0, 0), ldd, st)
+    if f2 is not None:
+        _lib.call("gprb_kff", kernel, f1.handle, f2.handle, p0, p1, float(zeta_ff), int(bool(use_tol)), float(tol),
+                  ff_mode, fa, fb, _at(K, 0, NE2), ld, _at(dK, 0, NE2), ldd, st)
+
+
 def k_total_device(kernel, p0, p1, zeta, side1, side2=None, use_tol=True, tol=1e-10, grad=False,
                    zeta_ef=None, zeta_ff=None, window=None, symmetric=True):
     """Build the covariance between two (energy Pack, force Pack) sides on the current CUDA device.
@@ -188,15 +260,10 @@ def k_total_device(kernel, p0, p1, zeta, side1, side2=None, use_tol=True, tol=1e
     [rows, NE2 + 3 NF2]; dK is dK/dl for RBF when grad=True, else None.
     """
     require_cuda()
-    e1, f1 = side1
     same = side2 is None
-    e2, f2 = side1 if same else side2
-    zeta_ef = zeta if zeta_ef is None else zeta_ef
-    zeta_ff = zeta if zeta_ff is None else zeta_ff
-    NE1 = e1.n_groups if e1 is not None else 0
-    NF1 = f1.n_groups if f1 is not None else 0
-    NE2 = e2.n_groups if e2 is not None else 0
-    NF2 = f2.n_groups if f2 is not None else 0
+    side2 = side1 if same else side2
+    NE1, NF1 = _sizes(side1)
+    NE2, NF2 = _sizes(side2)
     if window is None:
         (ea, eb), (fa, fb) = (0, NE1), (0, NF1)
     else:
@@ -204,47 +271,18 @@ def k_total_device(kernel, p0, p1, zeta, side1, side2=None, use_tol=True, tol=1e
     full = (ea, eb, fa, fb) == (0, NE1, 0, NF1)
     n_rows = (eb - ea) + 3 * (fb - fa)
     n_cols = NE2 + 3 * NF2
-    # zero-filled so that blocks without both sides (or empty windows) are defined
-    K = torch.zeros((n_rows, n_cols), dtype=F64, device="cuda")
-    dK = torch.zeros((n_rows, n_cols), dtype=F64, device="cuda") if grad else None
+    # every block that exists for the given sides is fully written by its builder
+    K = torch.empty((n_rows, n_cols), dtype=F64, device="cuda")
+    dK = torch.empty((n_rows, n_cols), dtype=F64, device="cuda") if grad else None
     if n_rows == 0 or n_cols == 0:
         return K, dK
-    ld = n_cols
-    st = stream()
-    esz = K.element_size()
-
-    def at(t, r, c):
-        return c_vp(0) if t is None else c_vp(t.data_ptr() + (r * ld + c) * esz)
-
     r_f = eb - ea          # first force row of the block
-    if e1 is not None and e2 is not None and eb > ea:
-        _lib.call("gprb_kee", kernel, e1.handle, e2.handle, p0, p1, float(zeta), ea, eb,
-                  at(K, 0, 0), ld, at(dK, 0, 0), ld, st)
-    if same and full and e1 is not None and f1 is not None:
-        # one pass writes K_ef and its transpose K_fe
-        _lib.call("gprb_kef", kernel, e1.handle, f1.handle, p0, p1, float(zeta_ef), 0, NF1,
-                  at(K, 0, NE2), ld, at(K, r_f, 0), ld, at(dK, 0, NE2), ld, at(dK, r_f, 0), ld, st)
-    else:
-        if e1 is not None and f2 is not None and eb > ea:
-            # rows = my energy groups, all force columns: compute the full-height block and keep my rows
-            if (ea, eb) == (0, NE1):
-                _lib.call("gprb_kef", kernel, e1.handle, f2.handle, p0, p1, float(zeta_ef), 0, NF2,
-                          at(K, 0, NE2), ld, c_vp(0), 0, at(dK, 0, NE2), ld, c_vp(0), 0, st)
-            else:
-                tmp = torch.zeros((NE1, 3 * NF2), dtype=F64, device="cuda")
-                dtmp = torch.zeros((NE1, 3 * NF2), dtype=F64, device="cuda") if grad else None
-                _lib.call("gprb_kef", kernel, e1.handle, f2.handle, p0, p1, float(zeta_ef), 0, NF2,
-                          ptr(tmp), 3 * NF2, c_vp(0), 0, ptr(dtmp), 3 * NF2, c_vp(0), 0, st)
-                K[:eb - ea, NE2:] = tmp[ea:eb]
-                if grad:
-                    dK[:eb - ea, NE2:] = dtmp[ea:eb]
-        if f1 is not None and e2 is not None and fb > fa:
-            _lib.call("gprb_kef", kernel, e2.handle, f1.handle, p0, p1, float(zeta_ef), fa, fb,
-                      c_vp(0), 0, at(K, r_f, 0), ld, c_vp(0), 0, at(dK, r_f, 0), ld, st)
-    if f1 is not None and f2 is not None and fb > fa:
-        mode = _lib.FF_SYMMETRIC if (same and full and symmetric) else _lib.FF_FULL
-        _lib.call("gprb_kff", kernel, f1.handle, f2.handle, p0, p1, float(zeta_ff), int(bool(use_tol)), float(tol),
-                  mode, fa, fb, at(K, r_f, NE2), ld, at(dK, r_f, NE2), ld, st)
+    one_pass = same and full and side1[0] is not None and side1[1] is not None
+    build_energy_rows(kernel, p0, p1, zeta, side1, side2, (ea, eb), K[:r_f], None if dK is None else dK[:r_f],
+                      zeta_ef=zeta_ef, kfe_rows=(K[r_f:], None if dK is None else dK[r_f:]) if one_pass else None)
+    mode = _lib.FF_SYMMETRIC if (same and full and symmetric) else _lib.FF_FULL
+    build_force_rows(kernel, p0, p1, zeta, side1, side2, (fa, fb), K[r_f:], None if dK is None else dK[r_f:],
+                     use_tol=use_tol, tol=tol, zeta_ef=zeta_ef, zeta_ff=zeta_ff, ff_mode=mode, skip_kfe=one_pass)
     return K, dK
 
 

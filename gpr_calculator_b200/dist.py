@@ -40,13 +40,18 @@ def split_groups(costs, parts):
     return bounds
 
 
-def row_windows(e_rows, f_rows, parts):
+def row_windows(e_rows, f_rows, parts, upper=False):
     """Per-rank windows ((e0,e1),(f0,f1)) over energy groups and force groups.
 
     Energy and force groups are partitioned independently so that every rank gets an equal share
-    of both block rows (the force block dominates: cost ~ rows of the centre)."""
+    of both block rows (the force block dominates: cost ~ rows of the centre).  upper=True balances
+    the trapezoids of an upper-triangle build (GPRB_FF_UPPER): force group I costs
+    n_I * sum_{J >= I} n_J."""
     eb = split_groups(e_rows, parts)
-    fb = split_groups(f_rows, parts)
+    f = np.asarray(f_rows, dtype=np.float64)
+    if upper and len(f):
+        f = f * np.cumsum(f[::-1])[::-1]
+    fb = split_groups(f, parts)
     return [((eb[r], eb[r + 1]), (fb[r], fb[r + 1])) for r in range(parts)]
 
 
@@ -63,19 +68,36 @@ def gather_rows(K_local, windows, NE, N, group=None):
     n_cols = K_local.shape[1]
     if size == 1:
         return K_local
-    counts = [(e1 - e0) + 3 * (f1 - f0) for (e0, e1), (f0, f1) in windows]
-    mx = max(counts)
-    # equal-sized exchange buffers (all_gather_into_tensor needs them); padding rows are dropped below
-    send = torch.zeros((mx, n_cols), dtype=K_local.dtype, device=K_local.device)
-    send[:counts[rank]] = K_local
-    recv = torch.empty((size * mx, n_cols), dtype=K_local.dtype, device=K_local.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
     K = torch.empty((N, n_cols), dtype=K_local.dtype, device=K_local.device)
-    for r, ((e0, e1), (f0, f1)) in enumerate(windows):
-        blk = recv[r * mx:r * mx + counts[r]]
-        ne = e1 - e0
-        K[e0:e1] = blk[:ne]
-        K[NE + 3 * f0:NE + 3 * f1] = blk[ne:]
+    (e0, e1), (f0, f1) = windows[rank]
+    K[e0:e1] = K_local[:e1 - e0]
+    K[NE + 3 * f0:NE + 3 * f1] = K_local[e1 - e0:]
+    gather_rows_inplace(K, windows, NE, group=group)
+    return K
+
+
+def gather_rows_inplace(K, windows, NE, group=None):
+    """In-place all-gather: every rank has written its own energy and force row slabs of the full
+    matrix K; on return every rank holds all rows.  The slabs are contiguous row ranges of the
+    row-major matrix, so each is sent from and received into K itself (no staging copies); uneven
+    slab sizes are handled by the backend (NCCL: grouped broadcasts)."""
+    rank, size = world()
+    if size == 1:
+        return K
+    for slabs in ([K[e0:e1] for (e0, e1), _ in windows], [K[NE + 3 * f0:NE + 3 * f1] for _, (f0, f1) in windows]):
+        if all(s.numel() == 0 for s in slabs):
+            continue
+        n0 = slabs[0].numel()
+        lo = slabs[0].data_ptr()
+        if n0 > 0 and all(s.numel() == n0 and s.data_ptr() == lo + r * n0 * K.element_size() for r, s in enumerate(slabs)):
+            # equal slabs tiling one contiguous range: a single all-gather straight into K
+            whole = K.view(-1)[(lo - K.data_ptr()) // K.element_size():][:size * n0]
+            dist.all_gather_into_tensor(whole, slabs[rank].reshape(-1).clone(), group=group)
+            continue
+        # uneven slabs (cost-balanced windows): one broadcast per owner, each received in place
+        for r, s in enumerate(slabs):
+            if s.numel():
+                dist.broadcast(s, src=r if group is None else dist.get_global_rank(group, r), group=group)
     return K
 
 

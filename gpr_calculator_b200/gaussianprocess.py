@@ -161,22 +161,44 @@ class GP():
     def _n_energy_rows(self, train_x=None):
         train_x = self.train_x if train_x is None else train_x
         e = train_x.get('energy', [])
+        if hasattr(e, "n_groups"):      # a device-resident Pack
+            return e.n_groups
         if isinstance(e, tuple):
             return len(e[-1])
         return len(e)
 
     def _build_K(self, grad, f_tol=1e-10):
-        """Training covariance (and dK/dl) on this device; row-block sharded when distributed."""
+        """Training covariance (and dK/dl) on this device; row-block sharded when distributed.
+
+        Returns (K [N, N], dK rows held by this rank or None, row ranges of those rows).
+        Multi-GPU (replaces RBF_mb.py:471-521): every rank writes its energy / force row slabs of
+        the full K in place (upper-triangle blocks only for K_ff), the slabs are all-gathered in
+        place and the force-force block is mirrored; dK/dl stays local to the rank."""
         rank, size = gdist.world()
-        if size == 1:
-            return self.kernel.k_total_device(self.train_x, None, f_tol=f_tol, grad=grad) + (None,)
         e, f = packs_of(self.train_x)
         NE = e.n_groups if e is not None else 0
-        windows = gdist.row_windows(e.indices if e is not None else [], f.indices if f is not None else [], size)
-        K_loc, dK_loc = self.kernel.k_total_device(self.train_x, None, f_tol=f_tol, grad=grad, window=windows[rank])
-        N = NE + 3 * (f.n_groups if f is not None else 0)
-        K = gdist.gather_rows(K_loc, windows, NE, N)
-        return K, dK_loc, (windows, NE)
+        NF = f.n_groups if f is not None else 0
+        N = NE + 3 * NF
+        if size == 1:
+            K, dK = self.kernel.k_total_device(self.train_x, None, f_tol=f_tol, grad=grad)
+            return K, dK, [(0, N)]
+        from .device import build_energy_rows, build_force_rows
+        args = self.kernel.cov_args(grad=grad, f_tol=f_tol)
+        has_dk = grad and args.pop("has_dk")
+        windows = gdist.row_windows(e.indices if e is not None else [], f.indices if f is not None else [], size, upper=True)
+        (e0, e1), (f0, f1) = windows[rank]
+        n_loc = (e1 - e0) + 3 * (f1 - f0)
+        K = torch.empty((N, N), dtype=F64, device="cuda")
+        dK = torch.zeros((n_loc, N), dtype=F64, device="cuda") if has_dk else None
+        ff = dict(use_tol=args.pop("use_tol"), tol=args.pop("tol"), zeta_ff=args.pop("zeta_ff"))
+        build_energy_rows(side1=(e, f), side2=(e, f), window=(e0, e1), K=K[e0:e1],
+                          dK=None if dK is None else dK[:e1 - e0], **args)
+        build_force_rows(side1=(e, f), side2=(e, f), window=(f0, f1), K=K[NE + 3 * f0:NE + 3 * f1],
+                         dK=None if dK is None else dK[e1 - e0:], ff_mode=_lib.FF_UPPER, **args, **ff)
+        gdist.gather_rows_inplace(K, windows, NE)
+        if NF:
+            _lib.call("gprb_symmetrize", c_vp(K.data_ptr() + (NE * N + NE) * 8), N, 3 * NF, stream())
+        return K, dK, [(e0, e1), (NE + 3 * f0, NE + 3 * f1)]
 
     def _factor(self, K, noise_e, noise_f):
         """K += noise; in-place Cholesky; alpha = K^-1 y.  Returns alpha (device vector)."""
@@ -214,7 +236,7 @@ class GP():
         kernel.update(kernel_params)
 
         is_rbf = isinstance(kernel, RBF_mb)
-        K, dK, shard = self._build_K(grad=eval_gradient)
+        K, dK, r_ranges = self._build_K(grad=eval_gradient)
         N = K.shape[0]
         NE = self._n_energy_rows()
         st = stream()
@@ -234,14 +256,10 @@ class GP():
         Kinv = torch.empty((N, N), dtype=F64, device="cuda")
         _lib.call("gprb_chol_inverse", ptr(K), N, N, ptr(Kinv), N, st)
         out = (ctypes_double * 2)()
-        # rows of dK held by this rank
-        if shard is None:
-            r_ranges = [(0, N)]
-        else:
-            windows, _ = shard
-            (e0, e1), (f0, f1) = windows[gdist.world()[0]]
-            r_ranges = [(e0, e1), (NE + 3 * f0, NE + 3 * f1)]
-        # 1/2 tr(W dK/dl) over my rows + 1/2 sum_i W_ii noise_i^2 (for the sigma term)
+        sharded = gdist.world()[1] > 1
+        # 1/2 tr(W dK/dl) over the rows of dK held by this rank (W, dK symmetric: columns j >= i,
+        # off-diagonal terms doubled -- the blocks left of the diagonal are not built when sharded)
+        # + 1/2 sum_i W_ii noise_i^2 (for the sigma term)
         g_l = 0.0
         half_w_noise = 0.0
         half_w_base = 0.0
@@ -250,24 +268,24 @@ class GP():
             if r1 > r0:
                 dptr = c_vp(0)
                 if is_rbf:
-                    dptr = c_vp(dK.data_ptr() + off * dK.shape[1] * 8)
+                    dptr = c_vp(dK.data_ptr() + off * dK.stride(0) * 8)
                 _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, dptr, N, NE,
-                          float(noise_e) ** 2, float(noise_f) ** 2, 0, out, st)
+                          float(noise_e) ** 2, float(noise_f) ** 2, 1, out, st)
                 g_l += out[0]
                 half_w_noise += out[1]
                 _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, c_vp(0), N, NE,
-                          2.0 * float(noise_e), 2.0 * float(noise_f), 0, out, st)
+                          2.0 * float(noise_e), 2.0 * float(noise_f), 1, out, st)
                 half_w_base += out[1]
             off += r1 - r0
         g_s0 = 0.0
         if not is_rbf:
             # Dot: dK/dsigma0 = 0.8 * 2 sigma^2 sigma0 on the E-E block only (dot_kernel.py:58)
             (r0, r1) = r_ranges[0]
-            r1 = min(r1, NE)            # energy rows held by this rank
+            r1 = min(r1, NE)            # energy rows held by this rank (the first range starts with them)
             if r1 > r0 and NE > 0:
                 _lib.call("gprb_w_block_sum", N, r0, r1, 0, NE, ptr(alpha), ptr(Kinv), N, out, st)
                 g_s0 = out[0] * (0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0)
-        if shard is not None:
+        if sharded:
             g_l, half_w_noise, half_w_base, g_s0 = gdist.all_reduce_sum([g_l, half_w_noise, half_w_base, g_s0], device="cuda")
         # 1/2 tr(W (2/sigma) K0), K0 = K - noise:  tr(W K) = y.alpha - N
         g_sigma = ((ya - N) - 2.0 * half_w_noise) / kernel.sigma

@@ -46,6 +46,13 @@ class Dot_mb():
         self.sigma, self.sigma0 = para[0], para[1]
 
     # ---- device entry points ------------------------------------------------------------------
+    def cov_args(self, grad=False, f_tol=1e-12):
+        """Arguments of device.build_energy_rows / build_force_rows (see the module docstring for the
+        zeta used by the E-F / F-F blocks)."""
+        z_cross = float(self.zeta) if grad else 2.0
+        return dict(kernel=_lib.DOT, p0=float(self.sigma), p1=float(self.sigma0), zeta=float(self.zeta), zeta_ef=z_cross,
+                    zeta_ff=z_cross, use_tol=False, tol=0.0, has_dk=False)
+
     def k_total_device(self, data1, data2=None, f_tol=1e-12, grad=False, window=None, symmetric=True):
         """(K, None).  grad selects which zeta the E-F / F-F blocks use (see module docstring);
         the gradient blocks themselves are closed-form (grad_terms)."""

@@ -48,6 +48,11 @@ class RBF_mb():
         self.sigma, self.l = para[0], para[1]
 
     # ---- device entry points ------------------------------------------------------------------
+    def cov_args(self, grad=False, f_tol=1e-10):
+        """Arguments of device.build_energy_rows / build_force_rows for this kernel (row-sharded builds)."""
+        return dict(kernel=_lib.RBF, p0=float(self.sigma), p1=float(self.l), zeta=float(self.zeta), zeta_ef=float(self.zeta),
+                    zeta_ff=float(self.zeta), use_tol=not grad, tol=f_tol, has_dk=True)
+
     def k_total_device(self, data1, data2=None, f_tol=1e-10, grad=False, window=None, symmetric=True):
         """(K, dK/dl) as CUDA tensors.  grad=True follows k_total_with_grad: no pair cut in K_ff
         (rbf_kernel.cpp:534); grad=False follows k_total: pair cut `dK_dD > f_tol` (:395)."""

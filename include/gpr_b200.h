@@ -44,6 +44,8 @@ enum { GPRB_FF_FULL = 0,      /* every (I,J) block of the window                
 int gprb_version(void);
 const char *gprb_last_error(void);   /* thread-local message of the last failing call */
 int gprb_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* number of CUDA kernels this library has launched in the process so far (bench.py's gpu_launches) */
+long long gprb_launch_count(void);
 
 /* ---- packing -------------------------------------------------------------------------------
  * Replaces utilities.list_to_tuple (utilities.py:340-390) + the per-call cffi marshalling and the
