@@ -38,37 +38,42 @@ extern std::atomic<long long> g_gprb_launches;
 
 // Device-resident packed side of a covariance block.
 //
-// Tile layout (the unit every kernel consumes): rows are padded per group to a multiple of 8 and
-// cut into tiles of 8 rows.  One tile stores, for each component c (0 = x^, 1..3 = A~ columns),
-// the 8 x (4*ks) operand slab in k-step-major order
+// Flat tile layout (the unit every kernel consumes): the rows of all groups are concatenated in
+// group order WITHOUT per-group padding and cut into tiles of 8 consecutive rows, so a tile may hold
+// the last rows of one group and the first rows of the next (only the tail of the pack is padded, to
+// a multiple of GPRB_CHUNK_TILES tiles).  One tile stores, for each component c (0 = x^, 1..3 = A~
+// columns), the 8 x (4*ks) operand slab in k-step-major order
 //        P[((tile*ncomp + c)*ks + kstep)*32 + row*4 + kk]      (k = 4*kstep + kk, zero padded)
 // so that the m8n8k4 fragment of (c, kstep) is the 32 consecutive doubles read by lane = row*4+kk:
 // one fully coalesced 256-byte access from global memory and a conflict-free one from shared
 // memory after a verbatim bulk copy.
+//
+// Tile record (GPRB_REC_INTS ints per tile, travels with the tile through the TMA ring):
+//   [0..7]  species of the 8 rows (-1 padding, -(z+2) dropped because |x| <= eps)
+//   [8]     number of group segments in the tile
+//   [10+2s] group id of segment s ; [11+2s] = row mask (bits 0..7) | 0x100 if the group ends in this tile
+#define GPRB_CHUNK_TILES 4         // tiles per column chunk (one TMA stage)
+#define GPRB_REC_INTS 28           // 112 bytes: a multiple of 16 for cp.async.bulk
+
 struct gprb_pack {
     int n_groups = 0, n_rows = 0, d = 0, ncols = 0, ncomp = 0, ks = 0, n_tiles = 0;
     int device = 0;
     std::vector<int> group_rows;   // host, [G]
-    std::vector<int> tile_ptr;     // host, [G+1]  first tile of each group
+    std::vector<int> row_ptr;      // host, [G+1]  first flat row of each group
     // per-group species histogram (non-dropped rows) for pair counting
     std::vector<std::map<int, long long>> species;
     bool species_ready = false;
     // device buffers
     double *P = nullptr;           // [n_tiles][ncomp][ks][32]
-    double *norm = nullptr;        // [n_tiles*8]  |x| of each padded row (0 for padding)
+    double *norm = nullptr;        // [n_tiles*8]  |x| of each row (0 for padding)
     int *elep = nullptr;           // [n_tiles*8]  species; -1 padding; -(z+2) dropped (|x|<=eps)
-    int *tile_group = nullptr;     // [n_tiles]
-    int *d_tile_ptr = nullptr;     // [G+1]
+    int *row_group = nullptr;      // [n_tiles*8]  group of each flat row (-1 padding)
+    int *tile_rec = nullptr;       // [n_tiles][GPRB_REC_INTS]
+    int *d_row_ptr = nullptr;      // [G+1]
     int *d_group_rows = nullptr;   // [G]
-    // column-side schedule: chunks of <= CH tiles that never straddle a group
-    int n_chunks = 0;
-    int4 *chunks = nullptr;        // device [n_chunks] {tile0, ntiles, group, last_of_group}
-    std::vector<int> group_chunk_ptr;   // host [G+1]
-    int *d_group_chunk_ptr = nullptr;
     // cached row-side schedule for the last window used (see cov_mma.cu)
     int sched_g0 = -1, sched_g1 = -1, sched_n = 0;
-    int4 *sched = nullptr;         // device [sched_n] {tile0, ntiles, group0, flags}
-    std::vector<int4> sched_host;
+    int4 *sched = nullptr;         // device [sched_n] {tile0, ntiles, entry_begin, n_entries}
+    int4 *sched_ent = nullptr;     // device entries {group, row0, row1 (block-local rows), shared}
+    std::vector<int4> sched_host, sched_ent_host;
 };
-
-#define GPRB_CHUNK_TILES 8         // max tiles per column chunk (8 x 8 KB = 64 KB of smem per stage)

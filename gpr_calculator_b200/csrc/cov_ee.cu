@@ -13,8 +13,8 @@
 namespace {
 
 struct EEParams {
-    const double *PA; const int *eleA; const int *tile_ptrA; const int *rowsA;
-    const double *PB; const int *eleB; const int *tile_ptrB; const int *rowsB;
+    const double *PA; const int *eleA; const int *row_ptrA; const int *rowsA;
+    const double *PB; const int *eleB; const int *row_ptrB; const int *rowsB;
     int ks, n_groupsB, grp_begin;
     double c_sigma2, c_i2l2, c_il3, c_sigma02, zeta;
     int zi, kernel;
@@ -29,7 +29,7 @@ __device__ __forceinline__ double pow_z(double s, double zeta, int zi) {
     return pow(s, zeta);
 }
 
-// element k of padded row r (tile-local) of an energy pack (ncomp = 1)
+// element k of flat row `prow` of an energy pack (ncomp = 1)
 __device__ __forceinline__ const double *row_base(const double *P, int ks, int prow) {
     return P + (size_t)(prow >> 3) * ks * 32 + (prow & 7) * 4;
 }
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) kee_kernel(const EEParams P) {
     const int I = P.grp_begin + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int kp = 4 * P.ks;
-    const int rowA0 = P.tile_ptrA[I] * 8;
+    const int rowA0 = P.row_ptrA[I];
     const int nA = P.rowsA[I];
     for (int a0 = 0; a0 < max(nA, 1); a0 += EE_MAX_SROWS) {
         const int na = max(0, min(EE_MAX_SROWS, nA - a0));
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) kee_kernel(const EEParams P) {
         __syncthreads();
         // column groups handled by this CTA: J = blockIdx.y*nwarps + warp, stride gridDim.y*nwarps
         for (int J = blockIdx.y * nwarps + warp; J < P.n_groupsB; J += gridDim.y * nwarps) {
-            const int rowB0 = P.tile_ptrB[J] * 8;
+            const int rowB0 = P.row_ptrB[J];
             const int nB = P.rowsB[J];
             double accK = 0.0, accD = 0.0;
             const int npairs = na * nB;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) kee_kernel(const EEParams P) {
 // diag(): energy rows, k(I,I) with norms (|x|+eps) and d = x1.x2 / (eps + n1 n2); no zero-norm drop.
 __global__ void __launch_bounds__(128) kee_diag_kernel(const EEParams P, const double *normA, double eps) {
     const int I = blockIdx.x;
-    const int row0 = P.tile_ptrA[I] * 8, n = P.rowsA[I];
+    const int row0 = P.row_ptrA[I], n = P.rowsA[I];
     double acc = 0.0;
     for (int pidx = threadIdx.x; pidx < n * n; pidx += blockDim.x) {
         const int a = pidx / n, b = pidx - a * n;
@@ -162,8 +162,8 @@ extern "C" int gprb_kee(int kernel, const gprb_pack *e1, const gprb_pack *e2, do
     EEParams P = {};
     int rc = fill(P, kernel, p0, p1, zeta);
     if (rc) return rc;
-    P.PA = e1->P; P.eleA = e1->elep; P.tile_ptrA = e1->d_tile_ptr; P.rowsA = e1->d_group_rows;
-    P.PB = e2->P; P.eleB = e2->elep; P.tile_ptrB = e2->d_tile_ptr; P.rowsB = e2->d_group_rows;
+    P.PA = e1->P; P.eleA = e1->elep; P.row_ptrA = e1->d_row_ptr; P.rowsA = e1->d_group_rows;
+    P.PB = e2->P; P.eleB = e2->elep; P.row_ptrB = e2->d_row_ptr; P.rowsB = e2->d_group_rows;
     P.ks = e1->ks; P.n_groupsB = e2->n_groups; P.grp_begin = grp_begin;
     P.K = K; P.ldk = ldk; P.dK = dK; P.lddk = lddk;
     const int nI = grp_end - grp_begin;
@@ -188,7 +188,7 @@ extern "C" int gprb_kee_diag(int kernel, const gprb_pack *e, double p0, double p
     EEParams P = {};
     int rc = fill(P, kernel, p0, p1, zeta);
     if (rc) return rc;
-    P.PA = e->P; P.eleA = e->elep; P.tile_ptrA = e->d_tile_ptr; P.rowsA = e->d_group_rows; P.ks = e->ks;
+    P.PA = e->P; P.eleA = e->elep; P.row_ptrA = e->d_row_ptr; P.rowsA = e->d_group_rows; P.ks = e->ks;
     P.K = out;
     kee_diag_kernel<<<e->n_groups, 128, 0, st>>>(P, e->norm, GPRB_EPS_NORM);
     GPRB_LAUNCHED();

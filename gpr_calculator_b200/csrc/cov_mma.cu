@@ -9,36 +9,52 @@
 //   s = x^_a.x^_b     p_c = A~_a[:,c].x^_b     q_e = x^_a.B~_b[:,e]     G_ce = A~_a[:,c].B~_b[:,e]
 //   K_ff[3I+c,3J+e] = sum_{a in I, b in J}  g (beta G_ce + gamma p_c q_e)
 // so a block of 8 x 8 atom pairs is 16 m8n8k4 accumulator tiles.  Rows are laid out
-// component-major (tile = 8 atoms of one component), which puts the complete 4x4 result of the
+// component-major (tile = 8 rows of one component), which puts the complete 4x4 result of the
 // pairs (a = lane/4, b = 2*(lane%4)+{0,1}) into the registers of ONE thread: the scalar epilogue
 // (exp, powers, rank-1 correction) needs no shuffles.
 //
-// Execution: one CTA = up to 8 warps = up to 8 row tiles covering whole groups (force centres);
-// each warp keeps its A fragments in registers for the whole kernel.  Column tiles are streamed
-// through a 2-stage shared-memory ring by 1-D TMA bulk copies (cp.async.bulk + mbarrier), one
-// chunk = the tiles of one column group (<= 8 tiles).  Per (I, J) the per-thread partial 3x3
-// sums are reduced by warp shuffles, then across the warps of the group through shared memory in
-// a fixed order (deterministic), and written once.  Groups larger than 64 rows are split over
-// CTAs and combined with fp64 atomics.
+// Generation 2 execution model:
+//  * FLAT tiles: rows of neighbouring groups share 8-row tiles on both sides, so no DMMA work is
+//    spent on per-group padding.  Column tiles carry a record of their group segments; a tile that
+//    straddles a group boundary is multiplied once and accumulated once per segment with masked
+//    weights.  Row tiles are handled by a segmented reduction (static per-thread predicates).
+//  * one CTA = 12 warps = 96 consecutive rows; the row tiles live in shared memory (TMA bulk copy
+//    at start) so that the kernel fits 168 registers and every scheduler has 3 warps to overlap
+//    one warp's scalar epilogue with the other warps' DMMAs (DMMA and DFMA share the FP64 pipe).
+//  * column tiles stream through a ring of TMA stages (cp.async.bulk + mbarrier); the warp that
+//    releases a stage last refills it — no producer warp and no CTA-wide barrier in the main loop.
+//  * flush at the end of a column group: transposing butterfly over the 4 lanes of a row, segmented
+//    suffix sum over the 8 rows of the warp, head rows to shared memory; the LAST warp to arrive
+//    adds the per-warp partials in a fixed order and writes the 3x3 block (deterministic).
+//    Row groups that continue in a neighbouring CTA are combined with fp64 atomics into the
+//    pre-zeroed output (two addends: still order independent).
 #include "common.cuh"
 #include <cstdint>
+#include <cmath>
 
 namespace {
 
-constexpr int WARPS = 8;
+constexpr int WARPS = 12;
 constexpr int THREADS = WARPS * 32;
+constexpr int STAGES = 2;
+constexpr int CH = GPRB_CHUNK_TILES;
+constexpr int REC = GPRB_REC_INTS;
+constexpr int MAXROWS = WARPS * 8;
 
 struct CovParams {
-    const double *PA; const int *eleA; const int *tile_groupA;
-    const int4 *sched;                 // row blocks {tile0, ntiles, group0, flags(bit0 = split group -> atomics)}
-    const double *PB; const int *eleB; const int4 *chunks; const int *gcpB; const int *group_rowsB;
-    int n_groupsB;
-    int n_splits;
-    double c_sigma2, c_i2l2, c_il, c_il3, zeta, tol, c_dot;   // c_dot = sigma^2 * zeta
+    const double *PA; const int *eleA; const int *row_groupA;
+    const int4 *sched; const int4 *sched_ent;
+    const double *PB; const int *recB; const int *row_ptrB; const int *group_rowsB;
+    int n_groupsB, n_splits, ks;
+    int win_r0, win_r1;                                   // row window on side A (flat rows)
+    // k1 = sigma^2/(2 l^2), kz = k1*zeta, c = 1/(2 l^2), h0 = 1/l^3 - 2/l ; Dot: c_dot = sigma^2 zeta
+    double k1, kz, c, c_il3, h0, zeta, tol, c_dot;
     int zi, use_tol, mode, grp_begin;
     double *K; long long ldk; double *dK; long long lddk;     // kff: K / dK/dl ; kfe: Kfe / dKfe
     double *K2; long long ldk2; double *dK2; long long lddk2; // kfe only: Kef / dKef (transposed copies)
 };
+
+__constant__ double c_exp2_tab[32];    // 2^(j/32)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -47,16 +63,27 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// Bounded waits: a protocol error must surface as a launch failure (trap), never as a hung GPU.
+constexpr long long SPIN_LIMIT_CYCLES = 8000000000LL;     // ~4 s at 1.9 GHz
+__device__ __noinline__ void spin_timeout(int what) {
+    printf("libgpr_b200: cov_mma_kernel wait %d timed out (block %d,%d thread %d)\n", what, blockIdx.x, blockIdx.y, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity))
+        if (clock64() - t0 > SPIN_LIMIT_CYCLES) spin_timeout(1);
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -67,9 +94,30 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// s^(zeta-2) with the integer cases the reference uses in practice (zeta = 2 default,
-// gaussianprocess.py:1027) kept off the pow() path
+// exp(x) for x <= 0 (the RBF exponent -(1-D)/(2 l^2)): 2^(k/32) table + degree-5 polynomial on
+// |r| <= ln2/64 (truncation 2e-15 relative).  10 FP64 instructions instead of the ~25 of exp().
+__device__ __forceinline__ double exp_neg(double x, const double *tab) {
+    if (x < -700.0) return 0.0;
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: low word = round-to-nearest integer
+    const double t = fma(x, 46.16624130844682903, MAGIC);    // 32 / ln 2
+    const int ki = __double2loint(t);
+    const double kf = t - MAGIC;
+    double r = fma(kf, -0x1.62e42fe000000p-6, x);            // ln2/32, high 29 bits (kf * hi is exact)
+    r = fma(kf, -0x1.f473de6af278fp-35, r);                   // ln2/32 - high part
+    double p = fma(r, 8.33333333333333322e-03, 4.16666666666666644e-02);
+    p = fma(p, r, 1.66666666666666657e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = tab[ki & 31] * p;
+    return __hiloint2double(__double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
+}
+
+// s^(zeta-2): ZI = 2 is compile-time (the reference's default zeta, gaussianprocess.py:1027);
+// ZI = 0 picks the small integer cases at run time and falls back to pow()
+template <int ZI>
 __device__ __forceinline__ double pow_zm2(double s, double zeta, int zi) {
+    if (ZI == 2) return 1.0;
     if (zi == 2) return 1.0;
     if (zi == 3) return s;
     if (zi == 4) return s * s;
@@ -78,258 +126,360 @@ __device__ __forceinline__ double pow_zm2(double s, double zeta, int zi) {
 }
 
 // Per-pair scalar weights.  out = w1*G + w2*p q^T ; grad: dout = u1*G + u2*p q^T
-// (for NB == 1: out_c = w1 * p_c, dout_c = u1 * p_c)
-template <int KERNEL, bool GRAD, bool FF>
-__device__ __forceinline__ void pair_weights(const CovParams &P, double s, bool valid,
+// (for NB == 1: out_c = w1 * p_c, dout_c = u1 * p_c).  `valid` may be cleared by the pair cut.
+template <int KERNEL, bool GRAD, bool FF, int ZI>
+__device__ __forceinline__ void pair_weights(const CovParams &P, const double *tab, double s, bool &valid,
                                              double &w1, double &w2, double &u1, double &u2) {
-    const double sm2 = pow_zm2(s, P.zeta, P.zi);
+    const double sm2 = pow_zm2<ZI>(s, P.zeta, P.zi);
     const double sm1 = s * sm2;
     if (KERNEL == GPRB_KERNEL_RBF) {
         const double D = s * sm1;
-        const double Kv = P.c_sigma2 * exp((D - 1.0) * P.c_i2l2);     // rbf_kernel.cpp:393
-        const double g = Kv * P.c_i2l2;                                // dK_dD (:394)
-        if (FF && !GRAD && P.use_tol) valid = valid && (g > P.tol);    // (:395) pair cut, non-grad only
-        const double gz = valid ? g * P.zeta : 0.0;
+        const double E = exp_neg(fma(D, P.c, -P.c), tab);             // exp(-(1-D)/(2l^2))  rbf_kernel.cpp:393
+        if (FF && !GRAD && P.use_tol) valid = valid && (E * P.k1 > P.tol);   // dK_dD > tol (:394-395), non-grad only
+        const double gz = E * P.kz;                                    // g * zeta
         w1 = gz * sm1;                                                 // g * beta
-        const double z2 = gz * P.zeta * sm1 * sm1;                     // g zeta^2 s^(2zeta-2)
-        if (FF) w2 = gz * (P.zeta - 1.0) * sm2 + z2 * P.c_i2l2;        // g * gamma
+        const double z2 = w1 * (P.zeta * sm1);                         // g zeta^2 s^(2zeta-2)
+        if (FF) w2 = (ZI == 2) ? fma(z2, P.c, gz) : fma(z2, P.c, gz * (P.zeta - 1.0) * sm2);   // g * gamma
         if (GRAD) {
-            const double h = (1.0 - D) * P.c_il3 - 2.0 * P.c_il;       // (:622-630), (:245-247)
+            const double h = fma(-P.c_il3, D, P.h0);                   // (1-D)/l^3 - 2/l   (:622-630, :245-247)
             u1 = w1 * h;
-            if (FF) u2 = w2 * h - z2 * P.c_il3;
+            if (FF) u2 = fma(w2, h, -(z2 * P.c_il3));
         }
     } else {   // Dot: sigma^2 zeta (s^(z-1) G + (z-1) s^(z-2) p q^T)   (dot_kernel.cpp:285-289, dot_kernel.py:256)
-        const double cz = valid ? P.c_dot : 0.0;
-        w1 = cz * sm1;
-        if (FF) w2 = cz * (P.zeta - 1.0) * sm2;
+        w1 = P.c_dot * sm1;
+        if (FF) w2 = P.c_dot * (P.zeta - 1.0) * sm2;
     }
 }
 
-template <int NB, int KS, int KERNEL, bool GRAD>
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI>
 __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) {
     constexpr bool FF = (NB == 4);
     constexpr int NOUT = FF ? 9 : 3;
-    constexpr int NTOT = GRAD ? 2 * NOUT : NOUT;
-    constexpr int TILE_DOUBLES = NB * KS * 32;
-    constexpr uint32_t TILE_BYTES = TILE_DOUBLES * 8;
+    constexpr int NT = GRAD ? 2 * NOUT : NOUT;
+    constexpr int N1 = (NT + 1) / 2, N2 = (N1 + 1) / 2;      // values left after each transposing butterfly step
+    const int KS = KS_T ? KS_T : P.ks;
+    const int a_tile_d = 4 * KS * 32, b_tile_d = NB * KS * 32;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sB = reinterpret_cast<double *>(smem_raw);                         // [2][CHUNK][TILE_DOUBLES]
-    int *sEle = reinterpret_cast<int *>(sB + 2 * GPRB_CHUNK_TILES * TILE_DOUBLES);   // [2][CHUNK*8]
-    double *sRed = reinterpret_cast<double *>(sEle + 2 * GPRB_CHUNK_TILES * 8);      // [2][WARPS][NTOT]
-    uint64_t *sBar = reinterpret_cast<uint64_t *>(sRed + 2 * WARPS * NTOT);          // [2]
-    int *sWg = reinterpret_cast<int *>(sBar + 2);                                     // [WARPS] local group of warp
+    double *sA = reinterpret_cast<double *>(smem_raw);                  // [WARPS][a_tile_d]
+    double *sB = sA + WARPS * a_tile_d;                                  // [STAGES][CH][b_tile_d]
+    double *sRow = sB + STAGES * CH * b_tile_d;                          // [2][MAXROWS][NT]
+    double *sTab = sRow + 2 * MAXROWS * NT;                              // [32]
+    int4 *sEnt = reinterpret_cast<int4 *>(sTab + 32);                    // [MAXROWS]
+    int *sRec = reinterpret_cast<int *>(sEnt + MAXROWS);                 // [STAGES][CH][REC]
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(sRec + STAGES * CH * REC);   // full[STAGES], A
+    int *sCnt = reinterpret_cast<int *>(sBar + STAGES + 1);              // consumed[STAGES], flushed[2], done
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int4 blk = P.sched[blockIdx.x];
-    const int tile0 = blk.x, ntiles = blk.y, g0 = blk.z;
-    const bool split = blk.w & 1;
-    const bool active = warp < ntiles;
-    const int atile = tile0 + (active ? warp : 0);
-    const int g1 = P.tile_groupA[tile0 + ntiles - 1] + 1;      // one past the last group of this block
+    const int tile0 = blk.x, ntiles = blk.y, ent0 = blk.z, nent = blk.w;
 
-    if (tid < WARPS) sWg[tid] = tid < ntiles ? P.tile_groupA[tile0 + tid] - g0 : -1;
+    // column group range of this CTA -> column tiles / chunks
+    int ga, gb;
+    {
+        const int G = P.n_groupsB;
+        ga = (int)((long long)G * blockIdx.y / P.n_splits);
+        gb = (int)((long long)G * (blockIdx.y + 1) / P.n_splits);
+        const int first_group = P.sched_ent[ent0].x, last_group = P.sched_ent[ent0 + nent - 1].x;
+        if (P.mode == GPRB_FF_SYMMETRIC || P.mode == GPRB_FF_UPPER) ga = max(ga, first_group);
+        if (P.mode == GPRB_FF_DIAG) { ga = max(ga, first_group); gb = min(gb, last_group + 1); }
+    }
+    if (gb <= ga) return;
+    const int cr0 = P.row_ptrB[ga], cr1 = P.row_ptrB[gb];
+    if (cr1 <= cr0) return;
+    const int tb0 = cr0 >> 3, tb1 = (cr1 + 7) >> 3;
+    const int c_begin = tb0 / CH, c_end = (tb1 + CH - 1) / CH;
+
+    if (tid < nent) sEnt[tid] = P.sched_ent[ent0 + tid];
+    if (tid < 32) sTab[tid] = c_exp2_tab[tid];
     if (tid == 0) {
-        mbar_init(&sBar[0], 1);
-        mbar_init(&sBar[1], 1);
+        for (int s = 0; s <= STAGES; s++) mbar_init(&sBar[s], 1);
+        for (int s = 0; s < STAGES + 3; s++) sCnt[s] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // column chunk range of this CTA
-    int c_begin, c_end;
-    {
-        const int G = P.n_groupsB;
-        int ga = (int)((long long)G * blockIdx.y / P.n_splits);
-        int gb = (int)((long long)G * (blockIdx.y + 1) / P.n_splits);
-        if (P.mode == GPRB_FF_SYMMETRIC || P.mode == GPRB_FF_UPPER) ga = max(ga, g0);
-        if (P.mode == GPRB_FF_DIAG) { ga = max(ga, g0); gb = min(gb, g1); }
-        if (gb < ga) gb = ga;
-        c_begin = P.gcpB[ga];
-        c_end = P.gcpB[gb];
-    }
-    if (c_begin >= c_end) return;
-
-    // A fragments: registers for the whole kernel
-    double af[4][KS];
-    {
-        const double *pa = P.PA + (size_t)atile * 4 * KS * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int k = 0; k < KS; k++) af[c][k] = active ? pa[(c * KS + k) * 32] : 0.0;
-    }
-    const int ele_a = active ? P.eleA[atile * 8 + (lane >> 2)] : -1;
-
+    const uint32_t b_chunk_bytes = (uint32_t)(CH * b_tile_d * 8), rec_chunk_bytes = (uint32_t)(CH * REC * 4);
     auto issue = [&](int ci, int buf) {
-        const int4 ch = P.chunks[ci];
-        const uint32_t bytes = (uint32_t)ch.y * TILE_BYTES, ebytes = (uint32_t)ch.y * 32u;
-        mbar_expect_tx(&sBar[buf], bytes + ebytes);
-        bulk_g2s(sB + (size_t)buf * GPRB_CHUNK_TILES * TILE_DOUBLES, P.PB + (size_t)ch.x * TILE_DOUBLES, bytes, &sBar[buf]);
-        bulk_g2s(sEle + buf * GPRB_CHUNK_TILES * 8, P.eleB + (size_t)ch.x * 8, ebytes, &sBar[buf]);
+        mbar_expect_tx(&sBar[buf], b_chunk_bytes + rec_chunk_bytes);
+        bulk_g2s(sB + (size_t)buf * CH * b_tile_d, P.PB + (size_t)ci * CH * b_tile_d, b_chunk_bytes, &sBar[buf]);
+        bulk_g2s(sRec + buf * CH * REC, P.recB + (size_t)ci * CH * REC, rec_chunk_bytes, &sBar[buf]);
     };
     if (tid == 0) {
-        issue(c_begin, 0);
-        if (c_begin + 1 < c_end) issue(c_begin + 1, 1);
+        const uint32_t a_bytes = (uint32_t)(ntiles * a_tile_d * 8);
+        mbar_expect_tx(&sBar[STAGES], a_bytes);
+        bulk_g2s(sA, P.PA + (size_t)tile0 * a_tile_d, a_bytes, &sBar[STAGES]);
+        for (int s = 0; s < STAGES; s++)
+            if (c_begin + s < c_end) issue(c_begin + s, s);
     }
+    if (warp >= ntiles) return;          // no CTA-wide barrier below this line
+    const int n_active = ntiles;
 
-    double out[NTOT];
+    // static per-thread row data: species, window, segment structure of the warp's 8 rows
+    const int ra = lane >> 2, q4 = lane & 3;
+    const int arow_local = warp * 8 + ra;
+    const int arow = (tile0 + warp) * 8 + ra;
+    int ele_a = P.eleA[arow];
+    if (arow < P.win_r0 || arow >= P.win_r1) ele_a = -1;
+    const int g_a = P.row_groupA[arow];
+    // (shuffles first, unconditionally: every lane must take part in a full-mask shuffle)
+    const int g_d1 = __shfl_down_sync(0xffffffffu, g_a, 4), g_d2 = __shfl_down_sync(0xffffffffu, g_a, 8);
+    const int g_d4 = __shfl_down_sync(0xffffffffu, g_a, 16), g_u1 = __shfl_up_sync(0xffffffffu, g_a, 4);
+    const bool p1 = (ra + 1 < 8) && (g_d1 == g_a);
+    const bool p2 = (ra + 2 < 8) && (g_d2 == g_a);
+    const bool p4 = (ra + 4 < 8) && (g_d4 == g_a);
+    const bool is_head = (ra == 0) || (g_u1 != g_a);
+
+    double out[NT];
 #pragma unroll
-    for (int i = 0; i < NTOT; i++) out[i] = 0.0;
-    int par = 0;
+    for (int i = 0; i < NT; i++) out[i] = 0.0;
+    int flush_idx = 0;
+
+    mbar_wait(&sBar[STAGES], 0);         // row tiles have landed
+    const double *pa = sA + (size_t)warp * a_tile_d + lane;
 
     for (int ci = c_begin; ci < c_end; ci++) {
-        const int it = ci - c_begin, buf = it & 1;
-        const int4 ch = P.chunks[ci];
-        mbar_wait(&sBar[buf], (it >> 1) & 1);
-        if (active) {
-            const double *tb = sB + (size_t)buf * GPRB_CHUNK_TILES * TILE_DOUBLES + lane;
-            const int *te = sEle + buf * GPRB_CHUNK_TILES * 8 + 2 * (lane & 3);
-            for (int t = 0; t < ch.y; t++, tb += TILE_DOUBLES, te += 8) {
-                double acc[4][NB][2];
+        const int it = ci - c_begin, buf = it % STAGES;
+        mbar_wait(&sBar[buf], (it / STAGES) & 1);
+        for (int tt = 0; tt < CH; tt++) {
+            const int t = ci * CH + tt;
+            if (t < tb0 || t >= tb1) continue;
+            const int *rec = sRec + (buf * CH + tt) * REC;
+            const double *pb = sB + (size_t)(buf * CH + tt) * b_tile_d + lane;
+
+            double acc[4][NB][2];
 #pragma unroll
-                for (int c = 0; c < 4; c++)
+            for (int c = 0; c < 4; c++)
 #pragma unroll
-                    for (int e = 0; e < NB; e++) { acc[c][e][0] = 0.0; acc[c][e][1] = 0.0; }
+                for (int e = 0; e < NB; e++) { acc[c][e][0] = 0.0; acc[c][e][1] = 0.0; }
+            if (KS_T) {
 #pragma unroll
-                for (int k = 0; k < KS; k++) {
-                    double bf[NB];
+                for (int k = 0; k < (KS_T ? KS_T : 1); k++) {
+                    double af[4], bf[NB];
 #pragma unroll
-                    for (int e = 0; e < NB; e++) bf[e] = tb[(e * KS + k) * 32];
+                    for (int c = 0; c < 4; c++) af[c] = pa[(c * KS_T + k) * 32];
+#pragma unroll
+                    for (int e = 0; e < NB; e++) bf[e] = pb[(e * KS_T + k) * 32];
 #pragma unroll
                     for (int c = 0; c < 4; c++)
 #pragma unroll
-                        for (int e = 0; e < NB; e++) dmma(acc[c][e][0], acc[c][e][1], af[c][k], bf[e]);
+                        for (int e = 0; e < NB; e++) dmma(acc[c][e][0], acc[c][e][1], af[c], bf[e]);
                 }
-                const int2 eb = *reinterpret_cast<const int2 *>(te);
+            } else {
+                for (int k = 0; k < KS; k++) {
+                    double af[4], bf[NB];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) af[c] = pa[(c * KS + k) * 32];
+#pragma unroll
+                    for (int e = 0; e < NB; e++) bf[e] = pb[(e * KS + k) * 32];
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int e = 0; e < NB; e++) dmma(acc[c][e][0], acc[c][e][1], af[c], bf[e]);
+                }
+            }
+
+            // weights of this thread's two pairs (a = ra, b = 2*q4 + j), once per tile
+            const int2 eb = *reinterpret_cast<const int2 *>(rec + 2 * q4);
+            double w1[2], w2[2], u1[2], u2[2];
+            bool valid[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int ele_b = j ? eb.y : eb.x;
+                valid[j] = (ele_a == ele_b) && (ele_a >= 0);
+                w2[j] = 0.0; u1[j] = 0.0; u2[j] = 0.0;
+                pair_weights<KERNEL, GRAD, FF, ZI>(P, sTab, acc[0][0][j], valid[j], w1[j], w2[j], u1[j], u2[j]);
+            }
+
+            const int nseg = rec[8];
+            for (int sg = 0; sg < nseg; sg++) {
+                const int J = rec[10 + 2 * sg], mf = rec[11 + 2 * sg];
+                if (J < ga || J >= gb) continue;
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const int ele_b = j ? eb.y : eb.x;
-                    const bool valid = (ele_a == ele_b) && (ele_a >= 0);
-                    double w1, w2 = 0.0, u1 = 0.0, u2 = 0.0;
-                    pair_weights<KERNEL, GRAD, FF>(P, acc[0][0][j], valid, w1, w2, u1, u2);
+                    const bool on = valid[j] && ((mf >> (2 * q4 + j)) & 1);
+                    const double W1 = on ? w1[j] : 0.0;
                     if (FF) {
+                        const double W2 = on ? w2[j] : 0.0, U1 = on ? u1[j] : 0.0, U2 = on ? u2[j] : 0.0;
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
                             const double pc = acc[c + 1][0][j];
-                            const double t2 = w2 * pc;
-                            const double t3 = GRAD ? u2 * pc : 0.0;
+                            const double t2 = W2 * pc;
+                            const double t3 = GRAD ? U2 * pc : 0.0;
 #pragma unroll
                             for (int e = 0; e < 3; e++) {
                                 const double G = acc[c + 1][(NB == 4) ? e + 1 : 0][j];
-                                const double q = acc[0][(NB == 4) ? e + 1 : 0][j];
-                                out[c * 3 + e] = fma(w1, G, fma(t2, q, out[c * 3 + e]));
-                                if (GRAD) out[NOUT + c * 3 + e] = fma(u1, G, fma(t3, q, out[NOUT + c * 3 + e]));
+                                const double qe = acc[0][(NB == 4) ? e + 1 : 0][j];
+                                out[c * 3 + e] = fma(W1, G, fma(t2, qe, out[c * 3 + e]));
+                                if (GRAD) out[NOUT + c * 3 + e] = fma(U1, G, fma(t3, qe, out[NOUT + c * 3 + e]));
                             }
                         }
                     } else {
+                        const double U1 = on ? u1[j] : 0.0;
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
                             const double pc = acc[c + 1][0][j];
-                            out[c] = fma(w1, pc, out[c]);
-                            if (GRAD) out[NOUT + c] = fma(u1, pc, out[NOUT + c]);
+                            out[c] = fma(W1, pc, out[c]);
+                            if (GRAD) out[NOUT + c] = fma(U1, pc, out[NOUT + c]);
                         }
                     }
                 }
-            }
-        }
-        if (ch.w) {   // last chunk of column group J: reduce over the warp
+                if (!(mf & 0x100)) continue;
+
+                // ---- flush: column group J is complete -------------------------------------------------
+                const int fb = flush_idx & 1;
+                if (flush_idx >= 2) {          // slot fb was used by flush_idx-2: wait until it has been summed
+                    if (lane == 0 && *reinterpret_cast<volatile int *>(&sCnt[STAGES + 2]) < flush_idx - 1) {
+                        const long long t0 = clock64();
+                        while (*reinterpret_cast<volatile int *>(&sCnt[STAGES + 2]) < flush_idx - 1)
+                            if (clock64() - t0 > SPIN_LIMIT_CYCLES) spin_timeout(2);
+                    }
+                    __syncwarp();
+                }
+                const bool b0 = lane & 1, b1 = lane & 2;
+                double wv[N1], zv[N2];
 #pragma unroll
-            for (int i = 0; i < NTOT; i++) {
-                double v = out[i];
+                for (int i = 0; i < N1; i++) {
+                    const double lo = out[2 * i], hi = (2 * i + 1 < NT) ? out[(2 * i + 1 < NT) ? 2 * i + 1 : 0] : 0.0;
+                    const double keep = b0 ? hi : lo, send = b0 ? lo : hi;
+                    wv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) sRed[(par * WARPS + warp) * NTOT + i] = v;
-                out[i] = 0.0;
-            }
-        }
-        __syncthreads();   // everyone is done with stage `buf`; sRed[par] is visible
-        if (tid == 0 && ci + 2 < c_end) issue(ci + 2, buf);
-        if (ch.w) {
-            const int J = ch.z;
-            const int ngl = g1 - g0;
-            if (tid < ngl * NTOT) {
-                const int lg = tid / NTOT, o = tid - lg * NTOT;
-                double v = 0.0;
+                for (int i = 0; i < N2; i++) {
+                    const double lo = wv[2 * i], hi = (2 * i + 1 < N1) ? wv[(2 * i + 1 < N1) ? 2 * i + 1 : 0] : 0.0;
+                    const double keep = b1 ? hi : lo, send = b1 ? lo : hi;
+                    zv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);      // row sum of value 4*i + q4
+                }
 #pragma unroll
-                for (int w = 0; w < WARPS; w++)
-                    if (sWg[w] == lg) v += sRed[(par * WARPS + w) * NTOT + o];
-                const int I = g0 + lg;
-                const bool isgrad = GRAD && o >= NOUT;
-                const int oo = isgrad ? o - NOUT : o;
-                if (FF) {
-                    const int c = oo / 3, e = oo - 3 * c;
-                    double *dst = isgrad ? P.dK : P.K;
-                    const long long ld = isgrad ? P.lddk : P.ldk;
-                    if (P.mode == GPRB_FF_DIAG) {
-                        if (I == J && c == e) {
-                            double *q = dst + 3 * (I - P.grp_begin) + c;
-                            if (split) atomicAdd(q, v); else *q = v;
-                        }
-                    } else {
-                        double *q = dst + (long long)(3 * (I - P.grp_begin) + c) * ld + 3 * J + e;
-                        if (split) atomicAdd(q, v); else *q = v;
-                        if (P.mode == GPRB_FF_SYMMETRIC && J >= g1) {
-                            double *qt = dst + (long long)(3 * J + e) * ld + 3 * I + c;
-                            if (split) atomicAdd(qt, v); else *qt = v;
+                for (int i = 0; i < N2; i++) {   // segmented suffix sum over the 8 rows: total lands on the head row
+                    double tv = __shfl_down_sync(0xffffffffu, zv[i], 4);
+                    zv[i] += p1 ? tv : 0.0;
+                    tv = __shfl_down_sync(0xffffffffu, zv[i], 8);
+                    zv[i] += p2 ? tv : 0.0;
+                    tv = __shfl_down_sync(0xffffffffu, zv[i], 16);
+                    zv[i] += p4 ? tv : 0.0;
+                }
+                if (is_head) {
+                    double *dst = sRow + (size_t)(fb * MAXROWS + arow_local) * NT + q4;
+#pragma unroll
+                    for (int i = 0; i < N2; i++)
+                        if (4 * i + q4 < NT) dst[4 * i] = zv[i];
+                }
+#pragma unroll
+                for (int i = 0; i < NT; i++) out[i] = 0.0;
+                __syncwarp();
+                int last = 0;
+                if (lane == 0) {
+                    __threadfence_block();
+                    last = ((atomicAdd(&sCnt[STAGES + fb], 1) + 1) % n_active) == 0;
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence_block();
+                    const int total = nent * NT;
+                    for (int idx = lane; idx < total; idx += 32) {
+                        const int en = idx / NT, o = idx - en * NT;
+                        const int4 E4 = sEnt[en];
+                        const int I = E4.x;
+                        const double *src = sRow + (size_t)fb * MAXROWS * NT + o;
+                        double v = src[E4.y * NT];
+                        for (int r = (E4.y & ~7) + 8; r < E4.z; r += 8) v += src[r * NT];
+                        const bool shared = E4.w != 0;
+                        const bool isgrad = GRAD && o >= NOUT;
+                        const int oo = isgrad ? o - NOUT : o;
+                        if (FF) {
+                            const int c = oo / 3, e = oo - 3 * c;
+                            double *dst = isgrad ? P.dK : P.K;
+                            const long long ld = isgrad ? P.lddk : P.ldk;
+                            if (P.mode == GPRB_FF_DIAG) {
+                                if (I == J && c == e) {
+                                    double *qd = dst + 3 * (I - P.grp_begin) + c;
+                                    if (shared) atomicAdd(qd, v); else *qd = v;
+                                }
+                            } else if (!((P.mode == GPRB_FF_SYMMETRIC || P.mode == GPRB_FF_UPPER) && J < I)) {
+                                double *qd = dst + (long long)(3 * (I - P.grp_begin) + c) * ld + 3 * J + e;
+                                if (shared) atomicAdd(qd, v); else *qd = v;
+                                if (P.mode == GPRB_FF_SYMMETRIC && J > I) {
+                                    double *qt = dst + (long long)(3 * J + e) * ld + 3 * I + c;
+                                    if (shared) atomicAdd(qt, v); else *qt = v;
+                                }
+                            }
+                        } else {
+                            // a side = force group I (window), b side = energy group J; K_ef = -(1/n_J) sum
+                            const int nJ = P.group_rowsB[J];
+                            const double val = nJ > 0 ? -v / (double)nJ : 0.0;
+                            const long long row = 3 * (I - P.grp_begin) + oo;
+                            double *fe = isgrad ? P.dK : P.K;
+                            const long long ldfe = isgrad ? P.lddk : P.ldk;
+                            double *ef = isgrad ? P.dK2 : P.K2;
+                            const long long ldef = isgrad ? P.lddk2 : P.ldk2;
+                            if (fe) { double *qd = fe + row * ldfe + J; if (shared) atomicAdd(qd, val); else *qd = val; }
+                            if (ef) { double *qd = ef + (long long)J * ldef + row; if (shared) atomicAdd(qd, val); else *qd = val; }
                         }
                     }
-                } else {
-                    // a side = force group I (window), b side = energy group J; K_ef = -(1/n_J) sum
-                    const int nJ = P.group_rowsB[J];
-                    const double val = nJ > 0 ? -v / (double)nJ : 0.0;
-                    const long long row = 3 * (I - P.grp_begin) + oo;
-                    double *fe = isgrad ? P.dK : P.K;
-                    const long long ldfe = isgrad ? P.lddk : P.ldk;
-                    double *ef = isgrad ? P.dK2 : P.K2;
-                    const long long ldef = isgrad ? P.lddk2 : P.ldk2;
-                    if (fe) { double *q = fe + row * ldfe + J; if (split) atomicAdd(q, val); else *q = val; }
-                    if (ef) { double *q = ef + (long long)J * ldef + row; if (split) atomicAdd(q, val); else *q = val; }
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        *reinterpret_cast<volatile int *>(&sCnt[STAGES + 2]) = flush_idx + 1;
+                    }
                 }
+                flush_idx++;
             }
-            par ^= 1;
+        }
+        // release the stage; the warp that arrives last refills it
+        __syncwarp();
+        if (lane == 0) {
+            const int old = atomicAdd(&sCnt[buf], 1);
+            if ((old + 1) % n_active == 0 && ci + STAGES < c_end) issue(ci + STAGES, buf);
         }
     }
 }
 
-template <int NB, int KS>
-constexpr size_t cov_smem_bytes(bool grad) {
-    return (size_t)2 * GPRB_CHUNK_TILES * NB * KS * 32 * 8 + 2 * GPRB_CHUNK_TILES * 8 * 4 +
-           (size_t)2 * WARPS * ((NB == 4 ? 9 : 3) * (grad ? 2 : 1)) * 8 + 16 + WARPS * 4 + 128;
+size_t cov_smem_bytes(int nb, int ks, bool grad) {
+    const int nt = (nb == 4 ? 9 : 3) * (grad ? 2 : 1);
+    return (size_t)(WARPS * 4 * ks * 32 + STAGES * CH * nb * ks * 32 + 2 * MAXROWS * nt + 32) * 8 +
+           (size_t)MAXROWS * 16 + (size_t)STAGES * CH * REC * 4 + (STAGES + 1) * 8 + (STAGES + 3) * 4 + 128;
 }
 
-// Row-side schedule: blocks of <= WARPS tiles made of whole groups; larger groups are split and flagged.
+// Row-side schedule for the window [g0, g1): blocks of <= WARPS consecutive flat tiles and, per block, the
+// groups it holds {group, first row, one past last row (block-local), continues in a neighbouring block}.
 int build_sched(gprb_pack *a, int g0, int g1, cudaStream_t st) {
     if (a->sched_g0 == g0 && a->sched_g1 == g1 && a->sched) return GPRB_OK;
-    std::vector<int4> s;
-    int g = g0;
-    while (g < g1) {
-        const int t0 = a->tile_ptr[g];
-        const int nt = a->tile_ptr[g + 1] - t0;
-        if (nt > WARPS) {
-            for (int o = 0; o < nt; o += WARPS) s.push_back(make_int4(t0 + o, nt - o < WARPS ? nt - o : WARPS, g, 1));
-            g++;
-            continue;
+    std::vector<int4> blocks, ents;
+    const int r0 = a->row_ptr[g0], r1 = a->row_ptr[g1];
+    if (r1 > r0) {
+        const int t0 = r0 / 8, t1 = (r1 + 7) / 8;
+        int g = g0;
+        for (int tb = t0; tb < t1; tb += WARPS) {
+            const int nt = t1 - tb < WARPS ? t1 - tb : WARPS;
+            const int lo = tb * 8 > r0 ? tb * 8 : r0, hi = (tb + nt) * 8 < r1 ? (tb + nt) * 8 : r1;
+            const int e0 = (int)ents.size();
+            while (g < g1 && a->row_ptr[g + 1] <= lo) g++;      // groups that ended before this block (or empty)
+            int gg = g;
+            while (gg < g1 && a->row_ptr[gg] < hi) {
+                const int s = a->row_ptr[gg] > lo ? a->row_ptr[gg] : lo;
+                const int e = a->row_ptr[gg + 1] < hi ? a->row_ptr[gg + 1] : hi;
+                if (e > s) {
+                    const int shared = (a->row_ptr[gg] < lo || a->row_ptr[gg + 1] > hi) ? 1 : 0;
+                    ents.push_back(make_int4(gg, s - tb * 8, e - tb * 8, shared));
+                }
+                gg++;
+            }
+            if ((int)ents.size() > e0) blocks.push_back(make_int4(tb, nt, e0, (int)ents.size() - e0));
         }
-        int ge = g + 1;
-        while (ge < g1 && a->tile_ptr[ge + 1] - t0 <= WARPS) ge++;
-        s.push_back(make_int4(t0, a->tile_ptr[ge] - t0, g, 0));
-        g = ge;
     }
     if (a->sched) { GPRB_CUDA(cudaFree(a->sched)); a->sched = nullptr; }
-    a->sched_host = s;
-    a->sched_n = (int)s.size();
+    if (a->sched_ent) { GPRB_CUDA(cudaFree(a->sched_ent)); a->sched_ent = nullptr; }
+    a->sched_host = blocks; a->sched_ent_host = ents;
+    a->sched_n = (int)blocks.size();
     a->sched_g0 = g0; a->sched_g1 = g1;
-    if (!s.empty()) {
-        GPRB_CUDA(cudaMalloc((void **)&a->sched, s.size() * sizeof(int4)));
-        GPRB_CUDA(cudaMemcpyAsync(a->sched, a->sched_host.data(), s.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    if (!blocks.empty()) {
+        GPRB_CUDA(cudaMalloc((void **)&a->sched, blocks.size() * sizeof(int4)));
+        GPRB_CUDA(cudaMalloc((void **)&a->sched_ent, ents.size() * sizeof(int4)));
+        GPRB_CUDA(cudaMemcpyAsync(a->sched, a->sched_host.data(), blocks.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        GPRB_CUDA(cudaMemcpyAsync(a->sched_ent, a->sched_ent_host.data(), ents.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
     }
     return GPRB_OK;
-}
-
-bool sched_has_split(const gprb_pack *a) {
-    for (auto &b : a->sched_host) if (b.w & 1) return true;
-    return false;
 }
 
 int integer_zeta(double zeta) {
@@ -337,43 +487,60 @@ int integer_zeta(double zeta) {
     return ((double)zi == zeta && zi >= 1 && zi <= 4) ? zi : -1;
 }
 
-template <int NB, int KS, int KERNEL, bool GRAD>
+int upload_tables() {
+    static bool done = false;
+    if (done) return GPRB_OK;
+    double tab[32];
+    for (int j = 0; j < 32; j++) tab[j] = std::exp2((double)j / 32.0);
+    GPRB_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof tab));
+    done = true;
+    return GPRB_OK;
+}
+
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI>
 int launch_cov(const CovParams &P, int n_blocks, cudaStream_t st) {
-    auto kern = cov_mma_kernel<NB, KS, KERNEL, GRAD>;
-    const size_t smem = cov_smem_bytes<NB, KS>(GRAD);
+    auto kern = cov_mma_kernel<NB, KS_T, KERNEL, GRAD, ZI>;
     static bool configured = false;
     if (!configured) {
-        GPRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GPRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_smem_bytes(NB, GPRB_MAX_KS, GRAD)));
         configured = true;
     }
     dim3 grid(n_blocks, P.n_splits);
-    kern<<<grid, THREADS, smem, st>>>(P);
+    kern<<<grid, THREADS, cov_smem_bytes(NB, P.ks, GRAD), st>>>(P);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }
 
-template <int NB, int KS>
+template <int NB, int KS_T, int ZI>
+int dispatch_kernel(int kernel, bool grad, const CovParams &P, int n_blocks, cudaStream_t st) {
+    if (kernel == GPRB_KERNEL_RBF) return grad ? launch_cov<NB, KS_T, GPRB_KERNEL_RBF, true, ZI>(P, n_blocks, st)
+                                               : launch_cov<NB, KS_T, GPRB_KERNEL_RBF, false, ZI>(P, n_blocks, st);
+    return launch_cov<NB, KS_T, GPRB_KERNEL_DOT, false, ZI>(P, n_blocks, st);
+}
+
+template <int NB>
 int dispatch_cov(int kernel, bool grad, const CovParams &P, int n_blocks, cudaStream_t st) {
-    if (kernel == GPRB_KERNEL_RBF) return grad ? launch_cov<NB, KS, GPRB_KERNEL_RBF, true>(P, n_blocks, st)
-                                               : launch_cov<NB, KS, GPRB_KERNEL_RBF, false>(P, n_blocks, st);
-    return launch_cov<NB, KS, GPRB_KERNEL_DOT, false>(P, n_blocks, st);
+    const bool z2 = P.zi == 2;
+    if (P.ks == 8) return z2 ? dispatch_kernel<NB, 8, 2>(kernel, grad, P, n_blocks, st) : dispatch_kernel<NB, 8, 0>(kernel, grad, P, n_blocks, st);
+    return z2 ? dispatch_kernel<NB, 0, 2>(kernel, grad, P, n_blocks, st) : dispatch_kernel<NB, 0, 0>(kernel, grad, P, n_blocks, st);
 }
 
 int fill_kernel_params(CovParams &P, int kernel, double p0, double p1, double zeta) {
     P.zeta = zeta;
     P.zi = integer_zeta(zeta);
-    P.c_sigma2 = p0 * p0;
     if (kernel == GPRB_KERNEL_RBF) {
         GPRB_REQUIRE(p1 > 0.0, "length scale l must be positive, got %g", p1);
-        P.c_i2l2 = 1.0 / (2.0 * p1 * p1);
-        P.c_il = 1.0 / p1;
+        P.c = 1.0 / (2.0 * p1 * p1);
+        P.k1 = p0 * p0 * P.c;
+        P.kz = P.k1 * zeta;
         P.c_il3 = 1.0 / (p1 * p1 * p1);
+        P.h0 = P.c_il3 - 2.0 / p1;
     } else {
-        P.c_i2l2 = P.c_il = P.c_il3 = 0.0;
+        P.c = P.k1 = P.kz = P.c_il3 = P.h0 = 0.0;
     }
     P.c_dot = p0 * p0 * zeta;
-    return GPRB_OK;
+    return upload_tables();
 }
 
 int choose_splits(int n_blocks, int n_groupsB) {
@@ -411,34 +578,27 @@ extern "C" int gprb_kff(int kernel, const gprb_pack *f1_, const gprb_pack *f2, d
     if (grp_begin == grp_end || f2->n_groups == 0) return GPRB_OK;
     int rc = build_sched(f1, grp_begin, grp_end, st);
     if (rc) return rc;
+    // the output is pre-zeroed: groups without rows stay zero and row groups shared by two CTAs are
+    // combined with atomics (UPPER leaves the blocks left of the diagonal zero)
     const int rows = 3 * (grp_end - grp_begin);
-    if (sched_has_split(f1)) {
-        if (mode == GPRB_FF_DIAG) {
-            GPRB_CUDA(cudaMemsetAsync(K, 0, (size_t)rows * sizeof(double), st));
-        } else {
-            GPRB_CUDA(cudaMemset2DAsync(K, ldk * sizeof(double), 0, (size_t)3 * f2->n_groups * sizeof(double), rows, st));
-            if (dK) GPRB_CUDA(cudaMemset2DAsync(dK, lddk * sizeof(double), 0, (size_t)3 * f2->n_groups * sizeof(double), rows, st));
-        }
+    if (mode == GPRB_FF_DIAG) {
+        GPRB_CUDA(cudaMemsetAsync(K, 0, (size_t)rows * sizeof(double), st));
+    } else {
+        GPRB_CUDA(cudaMemset2DAsync(K, ldk * sizeof(double), 0, (size_t)3 * f2->n_groups * sizeof(double), rows, st));
+        if (dK) GPRB_CUDA(cudaMemset2DAsync(dK, lddk * sizeof(double), 0, (size_t)3 * f2->n_groups * sizeof(double), rows, st));
     }
+    if (f1->sched_n == 0 || f2->n_rows == 0) return GPRB_OK;
     CovParams P = {};
     rc = fill_kernel_params(P, kernel, p0, p1, zeta);
     if (rc) return rc;
-    P.PA = f1->P; P.eleA = f1->elep; P.tile_groupA = f1->tile_group; P.sched = f1->sched;
-    P.PB = f2->P; P.eleB = f2->elep; P.chunks = f2->chunks; P.gcpB = f2->d_group_chunk_ptr;
-    P.group_rowsB = f2->d_group_rows; P.n_groupsB = f2->n_groups;
+    P.PA = f1->P; P.eleA = f1->elep; P.row_groupA = f1->row_group; P.sched = f1->sched; P.sched_ent = f1->sched_ent;
+    P.PB = f2->P; P.recB = f2->tile_rec; P.row_ptrB = f2->d_row_ptr; P.group_rowsB = f2->d_group_rows;
+    P.n_groupsB = f2->n_groups; P.ks = f1->ks;
+    P.win_r0 = f1->row_ptr[grp_begin]; P.win_r1 = f1->row_ptr[grp_end];
     P.tol = tol; P.use_tol = use_tol; P.mode = mode; P.grp_begin = grp_begin;
     P.K = K; P.ldk = ldk; P.dK = dK; P.lddk = lddk;
     P.n_splits = mode == GPRB_FF_DIAG ? 1 : choose_splits(f1->sched_n, f2->n_groups);
-    switch (f1->ks) {
-        case 8: return dispatch_cov<4, 8>(kernel, dK != nullptr, P, f1->sched_n, st);
-        case 7: return dispatch_cov<4, 7>(kernel, dK != nullptr, P, f1->sched_n, st);
-        case 6: return dispatch_cov<4, 6>(kernel, dK != nullptr, P, f1->sched_n, st);
-        case 5: return dispatch_cov<4, 5>(kernel, dK != nullptr, P, f1->sched_n, st);
-        case 4: return dispatch_cov<4, 4>(kernel, dK != nullptr, P, f1->sched_n, st);
-        case 3: return dispatch_cov<4, 3>(kernel, dK != nullptr, P, f1->sched_n, st);
-        case 2: return dispatch_cov<4, 2>(kernel, dK != nullptr, P, f1->sched_n, st);
-        default: return dispatch_cov<4, 1>(kernel, dK != nullptr, P, f1->sched_n, st);
-    }
+    return dispatch_cov<4>(kernel, dK != nullptr, P, f1->sched_n, st);
 }
 
 extern "C" int gprb_kef(int kernel, const gprb_pack *e, const gprb_pack *f_, double p0, double p1, double zeta,
@@ -462,31 +622,24 @@ extern "C" int gprb_kef(int kernel, const gprb_pack *e, const gprb_pack *f_, dou
     int rc = build_sched(f, grp_begin, grp_end, st);
     if (rc) return rc;
     const int rows = 3 * (grp_end - grp_begin);
-    if (sched_has_split(f)) {
+    {
         const size_t w = (size_t)e->n_groups * sizeof(double);
         if (Kfe) GPRB_CUDA(cudaMemset2DAsync(Kfe, ld_fe * sizeof(double), 0, w, rows, st));
         if (dKfe) GPRB_CUDA(cudaMemset2DAsync(dKfe, ld_dfe * sizeof(double), 0, w, rows, st));
         if (Kef) GPRB_CUDA(cudaMemset2DAsync(Kef, ld_ef * sizeof(double), 0, (size_t)rows * sizeof(double), e->n_groups, st));
         if (dKef) GPRB_CUDA(cudaMemset2DAsync(dKef, ld_def * sizeof(double), 0, (size_t)rows * sizeof(double), e->n_groups, st));
     }
+    if (f->sched_n == 0 || e->n_rows == 0) return GPRB_OK;
     CovParams P = {};
     rc = fill_kernel_params(P, kernel, p0, p1, zeta);
     if (rc) return rc;
-    P.PA = f->P; P.eleA = f->elep; P.tile_groupA = f->tile_group; P.sched = f->sched;
-    P.PB = e->P; P.eleB = e->elep; P.chunks = e->chunks; P.gcpB = e->d_group_chunk_ptr;
-    P.group_rowsB = e->d_group_rows; P.n_groupsB = e->n_groups;
+    P.PA = f->P; P.eleA = f->elep; P.row_groupA = f->row_group; P.sched = f->sched; P.sched_ent = f->sched_ent;
+    P.PB = e->P; P.recB = e->tile_rec; P.row_ptrB = e->d_row_ptr; P.group_rowsB = e->d_group_rows;
+    P.n_groupsB = e->n_groups; P.ks = f->ks;
+    P.win_r0 = f->row_ptr[grp_begin]; P.win_r1 = f->row_ptr[grp_end];
     P.mode = GPRB_FF_FULL; P.grp_begin = grp_begin;
     P.K = Kfe; P.ldk = ld_fe; P.dK = dKfe; P.lddk = ld_dfe;
     P.K2 = Kef; P.ldk2 = ld_ef; P.dK2 = dKef; P.lddk2 = ld_def;
     P.n_splits = choose_splits(f->sched_n, e->n_groups);
-    switch (f->ks) {
-        case 8: return dispatch_cov<1, 8>(kernel, grad, P, f->sched_n, st);
-        case 7: return dispatch_cov<1, 7>(kernel, grad, P, f->sched_n, st);
-        case 6: return dispatch_cov<1, 6>(kernel, grad, P, f->sched_n, st);
-        case 5: return dispatch_cov<1, 5>(kernel, grad, P, f->sched_n, st);
-        case 4: return dispatch_cov<1, 4>(kernel, grad, P, f->sched_n, st);
-        case 3: return dispatch_cov<1, 3>(kernel, grad, P, f->sched_n, st);
-        case 2: return dispatch_cov<1, 2>(kernel, grad, P, f->sched_n, st);
-        default: return dispatch_cov<1, 1>(kernel, grad, P, f->sched_n, st);
-    }
+    return dispatch_cov<1>(kernel, grad, P, f->sched_n, st);
 }

@@ -35,24 +35,25 @@ extern "C" int gprb_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     return GPRB_OK;
 }
 
-// One warp per padded row.  HBM-bound: reads 8*d*(1+ncols) bytes and writes 8*4ks*(1+ncols) per row.
-__global__ void prep_rows_kernel(int n_padded, int d, int ncols, int ks, double norm_eps,
+// One warp per row of the flat tile layout (rows >= n_rows are tail padding).
+// HBM-bound: reads 8*d*(1+ncols) bytes and writes 8*4ks*(1+ncols) per row.
+__global__ void prep_rows_kernel(int n_padded, int n_rows, int d, int ncols, int ks, double norm_eps,
                                  const double *__restrict__ x, const double *__restrict__ dxdr,
-                                 const int *__restrict__ ele, const int *__restrict__ src_row,
+                                 const int *__restrict__ ele,
                                  double *__restrict__ P, double *__restrict__ norm_out,
-                                 int *__restrict__ elep) {
+                                 int *__restrict__ elep, int *__restrict__ tile_rec) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= n_padded) return;
     const int ncomp = 1 + ncols;
     const int tile = warp >> 3, r = warp & 7;
     const int kp = 4 * ks;
-    const int src = src_row[warp];
+    const int src = warp < n_rows ? warp : -1;
     double *Pt = P + (size_t)tile * ncomp * ks * 32;
     if (src < 0) {   // padding row
         for (int c = 0; c < ncomp; c++)
             for (int k = lane; k < kp; k += 32) Pt[((size_t)c * ks + (k >> 2)) * 32 + r * 4 + (k & 3)] = 0.0;
-        if (lane == 0) { norm_out[warp] = 0.0; elep[warp] = -1; }
+        if (lane == 0) { norm_out[warp] = 0.0; elep[warp] = -1; tile_rec[(size_t)tile * GPRB_REC_INTS + r] = -1; }
         return;
     }
     const double *xr = x + (size_t)src * d;
@@ -86,7 +87,9 @@ __global__ void prep_rows_kernel(int n_padded, int d, int ncols, int ks, double 
     if (lane == 0) {
         norm_out[warp] = n - norm_eps;
         const int z = ele[src];
-        elep[warp] = dropped ? -(z + 2) : z;
+        const int code = dropped ? -(z + 2) : z;
+        elep[warp] = code;
+        tile_rec[(size_t)tile * GPRB_REC_INTS + r] = code;
     }
 }
 
@@ -109,9 +112,8 @@ static int stage_input(const T *any, size_t count, const T **dev, T **owned, cud
 
 extern "C" void gprb_pack_destroy(gprb_pack *p) {
     if (!p) return;
-    cudaFree(p->P); cudaFree(p->norm); cudaFree(p->elep); cudaFree(p->tile_group);
-    cudaFree(p->d_tile_ptr); cudaFree(p->d_group_rows); cudaFree(p->chunks);
-    cudaFree(p->d_group_chunk_ptr); cudaFree(p->sched);
+    cudaFree(p->P); cudaFree(p->norm); cudaFree(p->elep); cudaFree(p->row_group); cudaFree(p->tile_rec);
+    cudaFree(p->d_row_ptr); cudaFree(p->d_group_rows); cudaFree(p->sched); cudaFree(p->sched_ent);
     delete p;
 }
 
@@ -129,59 +131,54 @@ extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_
     GPRB_CUDA(cudaGetDevice(&p->device));
     p->n_groups = n_groups; p->d = d; p->ncols = ncols; p->ncomp = 1 + ncols; p->ks = (d + 3) / 4;
     p->group_rows.assign(group_rows_host, group_rows_host + n_groups);
-    p->tile_ptr.resize(n_groups + 1);
-    p->group_chunk_ptr.resize(n_groups + 1);
+    p->row_ptr.resize(n_groups + 1);
     long long rows = 0;
-    int tiles = 0;
-    std::vector<int4> chunks;
     for (int g = 0; g < n_groups; g++) {
         int ng = p->group_rows[g];
         if (ng < 0) { delete p; GPRB_REQUIRE(false, "gprb_pack_create: negative group size"); }
-        p->tile_ptr[g] = tiles;
-        p->group_chunk_ptr[g] = (int)chunks.size();
-        int nt = ng > 0 ? (ng + GPRB_TILE_ROWS - 1) / GPRB_TILE_ROWS : 1;   // empty groups keep one padding tile
-        for (int t0 = 0; t0 < nt; t0 += GPRB_CHUNK_TILES) {
-            int n = nt - t0 < GPRB_CHUNK_TILES ? nt - t0 : GPRB_CHUNK_TILES;
-            chunks.push_back(make_int4(tiles + t0, n, g, t0 + n == nt ? 1 : 0));
-        }
-        tiles += nt;
+        p->row_ptr[g] = (int)rows;
         rows += ng;
     }
-    p->tile_ptr[n_groups] = tiles;
-    p->group_chunk_ptr[n_groups] = (int)chunks.size();
-    p->n_tiles = tiles; p->n_rows = (int)rows; p->n_chunks = (int)chunks.size();
+    if (rows > 2000000000LL) { delete p; GPRB_REQUIRE(false, "gprb_pack_create: too many rows"); }
+    p->row_ptr[n_groups] = (int)rows;
+    int tiles = (int)((rows + GPRB_TILE_ROWS - 1) / GPRB_TILE_ROWS);
+    tiles = (tiles + GPRB_CHUNK_TILES - 1) / GPRB_CHUNK_TILES * GPRB_CHUNK_TILES;
+    p->n_tiles = tiles; p->n_rows = (int)rows;
     if (rows > 0 && (x_any == nullptr || ele_any == nullptr)) { delete p; GPRB_REQUIRE(false, "gprb_pack_create: x/ele NULL"); }
 
     const int n_padded = tiles * GPRB_TILE_ROWS;
-    std::vector<int> src(n_padded, -1), tgroup(tiles, 0);
-    {
-        int r = 0;
-        for (int g = 0; g < n_groups; g++) {
-            for (int t = p->tile_ptr[g]; t < p->tile_ptr[g + 1]; t++) tgroup[t] = g;
-            for (int i = 0; i < p->group_rows[g]; i++) src[p->tile_ptr[g] * GPRB_TILE_ROWS + i] = r++;
+    // per-row group ids and per-tile segment records (species slots are filled by the prep kernel)
+    std::vector<int> rgroup(n_padded, -1), rec((size_t)tiles * GPRB_REC_INTS, 0);
+    for (int g = 0; g < n_groups; g++)
+        for (int r = p->row_ptr[g]; r < p->row_ptr[g + 1]; r++) rgroup[r] = g;
+    for (int t = 0; t < tiles; t++) {
+        int *R = rec.data() + (size_t)t * GPRB_REC_INTS;
+        int nseg = 0;
+        for (int r = 0; r < GPRB_TILE_ROWS; r++) {
+            const int g = rgroup[t * GPRB_TILE_ROWS + r];
+            if (g < 0) break;                                   // tail padding
+            if (nseg == 0 || R[10 + 2 * (nseg - 1)] != g) { R[10 + 2 * nseg] = g; R[11 + 2 * nseg] = 0; nseg++; }
+            R[11 + 2 * (nseg - 1)] |= 1 << r;
+            if (t * GPRB_TILE_ROWS + r == p->row_ptr[g + 1] - 1) R[11 + 2 * (nseg - 1)] |= 0x100;
         }
+        R[8] = nseg;
     }
     if (tiles == 0) { *out = p; return GPRB_OK; }
 
-    int *d_src = nullptr;
     const size_t pbytes = (size_t)tiles * p->ncomp * p->ks * 32 * sizeof(double);
 #define PK_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { gprb_set_error("%s:%d CUDA error %s", __FILE__, __LINE__, cudaGetErrorString(_e)); gprb_pack_destroy(p); return GPRB_ERR_CUDA; } } while (0)
     PK_CUDA(cudaMalloc((void **)&p->P, pbytes));
     PK_CUDA(cudaMalloc((void **)&p->norm, (size_t)n_padded * sizeof(double)));
     PK_CUDA(cudaMalloc((void **)&p->elep, (size_t)n_padded * sizeof(int)));
-    PK_CUDA(cudaMalloc((void **)&p->tile_group, (size_t)tiles * sizeof(int)));
-    PK_CUDA(cudaMalloc((void **)&p->d_tile_ptr, (size_t)(n_groups + 1) * sizeof(int)));
+    PK_CUDA(cudaMalloc((void **)&p->row_group, (size_t)n_padded * sizeof(int)));
+    PK_CUDA(cudaMalloc((void **)&p->tile_rec, rec.size() * sizeof(int)));
+    PK_CUDA(cudaMalloc((void **)&p->d_row_ptr, (size_t)(n_groups + 1) * sizeof(int)));
     PK_CUDA(cudaMalloc((void **)&p->d_group_rows, (size_t)(n_groups > 0 ? n_groups : 1) * sizeof(int)));
-    PK_CUDA(cudaMalloc((void **)&p->chunks, chunks.size() * sizeof(int4)));
-    PK_CUDA(cudaMalloc((void **)&p->d_group_chunk_ptr, (size_t)(n_groups + 1) * sizeof(int)));
-    PK_CUDA(cudaMallocAsync((void **)&d_src, (size_t)n_padded * sizeof(int), st));
-    PK_CUDA(cudaMemcpyAsync(d_src, src.data(), (size_t)n_padded * sizeof(int), cudaMemcpyHostToDevice, st));
-    PK_CUDA(cudaMemcpyAsync(p->tile_group, tgroup.data(), (size_t)tiles * sizeof(int), cudaMemcpyHostToDevice, st));
-    PK_CUDA(cudaMemcpyAsync(p->d_tile_ptr, p->tile_ptr.data(), (size_t)(n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(p->row_group, rgroup.data(), (size_t)n_padded * sizeof(int), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(p->tile_rec, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(p->d_row_ptr, p->row_ptr.data(), (size_t)(n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     if (n_groups > 0)
         PK_CUDA(cudaMemcpyAsync(p->d_group_rows, p->group_rows.data(), (size_t)n_groups * sizeof(int), cudaMemcpyHostToDevice, st));
-    PK_CUDA(cudaMemcpyAsync(p->chunks, chunks.data(), chunks.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-    PK_CUDA(cudaMemcpyAsync(p->d_group_chunk_ptr, p->group_chunk_ptr.data(), (size_t)(n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
 
     const double *dx = nullptr, *ddx = nullptr; const int *de = nullptr;
     double *ox = nullptr, *odx = nullptr; int *oe = nullptr;
@@ -192,16 +189,15 @@ extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_
     {
         const int threads = 256, wpb = threads / 32;
         const int blocks = (n_padded + wpb - 1) / wpb;
-        prep_rows_kernel<<<blocks, threads, 0, st>>>(n_padded, d, ncols, p->ks, norm_eps, dx, ddx, de, d_src,
-                                                     p->P, p->norm, p->elep);
+        prep_rows_kernel<<<blocks, threads, 0, st>>>(n_padded, p->n_rows, d, ncols, p->ks, norm_eps, dx, ddx, de,
+                                                     p->P, p->norm, p->elep, p->tile_rec);
         GPRB_LAUNCHED();
         PK_CUDA(cudaGetLastError());
     }
     if (ox) PK_CUDA(cudaFreeAsync(ox, st));
     if (odx) PK_CUDA(cudaFreeAsync(odx, st));
     if (oe) PK_CUDA(cudaFreeAsync(oe, st));
-    PK_CUDA(cudaFreeAsync(d_src, st));
-    // the host vectors (src, tgroup, chunks) die at return: pageable H2D copies have been staged by then,
+    // the host vectors (rgroup, rec) die at return: pageable H2D copies have been staged by then,
     // but make that explicit and surface asynchronous faults of the prep kernel here.
     PK_CUDA(cudaStreamSynchronize(st));
 #undef PK_CUDA
@@ -225,7 +221,7 @@ static int ensure_species(gprb_pack *p) {
     if (!e.empty()) GPRB_CUDA(cudaMemcpy(e.data(), p->elep, e.size() * sizeof(int), cudaMemcpyDeviceToHost));
     p->species.assign(p->n_groups, {});
     for (int g = 0; g < p->n_groups; g++)
-        for (int r = p->tile_ptr[g] * GPRB_TILE_ROWS; r < p->tile_ptr[g + 1] * GPRB_TILE_ROWS; r++)
+        for (int r = p->row_ptr[g]; r < p->row_ptr[g + 1]; r++)
             if (e[r] >= 0) p->species[g][e[r]]++;
     p->species_ready = true;
     return GPRB_OK;
