@@ -345,21 +345,31 @@ def main():
             gp._alpha_dev = gp._factor(K, NOISE_E, NOISE_F)
             gp._L_dev, gp._Kinv_dev = K, None
             gp.set_K_inv()
-            tests = [a for a, _, _ in syn.structures(8, nrep, seed0 + 1000)]
+            n_test = 64
+            tests = [a for a, _, _ in syn.structures(n_test, nrep, seed0 + 1000)]
             for a in tests[:2]:
                 gp.predict_structure(a, stress=False, return_std=True, f_tol=1e-12)
             barrier()
             t0 = time.perf_counter()
-            for a in tests:
-                gp.predict_structure(a, stress=False, return_std=True, f_tol=1e-12)
+            for a in tests[:8]:
+                single = gp.predict_structure(a, stress=False, return_std=True, f_tol=1e-12)
             barrier()
-            with_io = len(tests) / (time.perf_counter() - t0)
+            single_ms = (time.perf_counter() - t0) / 8 * 1e3
+            gp.predict_structures(tests[:32], return_std=True, f_tol=1e-12, batch=32)
+            barrier()
+            t0 = time.perf_counter()
+            res = gp.predict_structures(tests, return_std=True, f_tol=1e-12, batch=32)
+            barrier()
+            with_io = n_test / (time.perf_counter() - t0)
+            assert abs(res[7][0] - single[0]) <= 1e-8 and np.abs(res[7][1] - single[1]).max() <= 1e-8
         except Exception as exc:      # the prediction leg must not hide the covariance numbers
             result["predict_error"] = repr(exc)
         if with_io is not None:
             result["predict"] = {"value": with_io * world, "unit": "structures/s", "n_train": N, "atoms": len(tests[0]),
-                                 "call": "GP.predict_structure(atoms, stress=False, return_std=True): SO3 + K* + mean + std, "
-                                         "host Atoms in, numpy E/F/std out; replicas over ranks"}
+                                 "single_call_ms": single_ms,
+                                 "call": "GP.predict_structures(list of Atoms, return_std=True, batch=32): SO3 + K* + mean + std on "
+                                         "device, host Atoms in, numpy E/F/std out; every rank predicts its own share (replicas); "
+                                         "single_call_ms = one GP.predict_structure(atoms, stress=False, return_std=True)"}
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

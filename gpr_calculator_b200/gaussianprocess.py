@@ -184,7 +184,7 @@ class GP():
             return K, dK, [(0, N)]
         from .device import build_energy_rows, build_force_rows
         args = self.kernel.cov_args(grad=grad, f_tol=f_tol)
-        has_dk = grad and args.pop("has_dk")
+        has_dk = args.pop("has_dk") and grad
         windows = gdist.row_windows(e.indices if e is not None else [], f.indices if f is not None else [], size, upper=True)
         (e0, e1), (f0, f1) = windows[rank]
         n_loc = (e1 - e0) + 3 * (f1 - f0)
@@ -365,12 +365,18 @@ class GP():
 
     def _predict_device(self, X, train_x, f_tol, return_std):
         """K* on device, mean and variance (gaussianprocess.py:338, 368-377 / 880, 904-908)."""
-        K_trans, _ = self.kernel.k_total_device(X, train_x, f_tol=f_tol, grad=False)
+        e, f = packs_of(X)                       # packed once, shared by K* and the prior variance
+        Xp = {}
+        if e is not None:
+            Xp["energy"] = e
+        if f is not None:
+            Xp["force"] = f
+        K_trans, _ = self.kernel.k_total_device(Xp, train_x, f_tol=f_tol, grad=False)
         m, N = K_trans.shape
         mean = torch.empty(m, dtype=F64, device="cuda")
         var = diag = work = None
         if return_std:
-            diag = self.kernel.diag_device(X)
+            diag = self.kernel.diag_device(X if isinstance(self.kernel, Dot_mb) else Xp, _packed_ok=True)
             var = torch.empty(m, dtype=F64, device="cuda")
             work = torch.empty((m, N), dtype=F64, device="cuda")
             self.set_K_inv()
@@ -669,14 +675,21 @@ class GP():
         if stress:
             raise NotImplementedError("stress prediction is not part of the B200 hot path yet (SURVEY.md §8f); "
                                       "call predict_structure(struc, stress=False, ...)")
-        d = self.descriptor.calculate(struc, use_mpi=True)
-        ele = atomic_numbers(d['elements'])
-        fix_ids = self._get_fixed_atoms(struc)
-        free_ids = [i for i in range(len(struc)) if i not in set(fix_ids)]
-        data = {"energy": list_to_tuple([(d['x'], ele)], mode='energy')}
-        data["force"] = [force_rows(d, ele, i) for i in free_ids]
-        if len(free_ids) == 0:
-            del data["force"]
+        fix_ids = set(self._get_fixed_atoms(struc))
+        free_ids = [i for i in range(len(struc)) if i not in fix_ids]
+        if hasattr(self.descriptor, "calculate_batch"):
+            # descriptors stay on the device: rows are gathered there (batch.rows_from_batch)
+            from .batch import rows_from_batch
+            E_t, F_t = rows_from_batch(self.descriptor.calculate_batch([struc], to_host=False), [free_ids])
+            data = {"energy": E_t}
+            if F_t is not None:
+                data["force"] = F_t
+        else:
+            d = self.descriptor.calculate(struc, use_mpi=True)
+            ele = atomic_numbers(d['elements'])
+            data = {"energy": list_to_tuple([(d['x'], ele)], mode='energy')}
+            if len(free_ids) > 0:
+                data["force"] = [force_rows(d, ele, i) for i in free_ids]
 
         train_x = self.get_train_x()
         _, mean, var = self._predict_device(data, train_x, f_tol, return_std)
@@ -699,6 +712,45 @@ class GP():
             F_std[free_ids] = y_std[1:].reshape([len(free_ids), 3])
             return E, F, S, E_std, F_std
         return E, F, S
+
+    def predict_structures(self, strucs, return_std=False, f_tol=1e-8, batch=32):
+        """Batched predict_structure(stress=False): descriptors, K*, mean and variance of `batch`
+        structures per device pass (the "predict 10k structures" path of the benchmark).
+
+        Returns a list of (E, F, None) or (E, F, None, E_std, F_std) tuples, one per structure, equal to
+        what predict_structure returns for each of them."""
+        require_cuda()
+        from .batch import rows_from_batch
+        if self.base_potential is not None:
+            raise NotImplementedError("base potentials are outside the B200 hot path")
+        train_x = self.get_train_x()
+        out = []
+        for s0 in range(0, len(strucs), batch):
+            part = strucs[s0:s0 + batch]
+            free = []
+            for st_ in part:
+                fixed = set(self._get_fixed_atoms(st_))
+                free.append([i for i in range(len(st_)) if i not in fixed])
+            E_t, F_t = rows_from_batch(self.descriptor.calculate_batch(part, to_host=False), free)
+            data = {"energy": E_t}
+            if F_t is not None:
+                data["force"] = F_t
+            _, mean, var = self._predict_device(data, train_x, f_tol, return_std)
+            y = mean.cpu().numpy()
+            sd = np.sqrt(var.cpu().numpy()) if return_std else None
+            pos = len(part)
+            for k, st_ in enumerate(part):
+                n, nf = len(st_), len(free[k])
+                F = np.zeros((n, 3))
+                F[free[k]] = y[pos:pos + 3 * nf].reshape(nf, 3)
+                if return_std:
+                    F_std = np.zeros((n, 3))
+                    F_std[free[k]] = sd[pos:pos + 3 * nf].reshape(nf, 3)
+                    out.append((y[k] * n, F, None, sd[k], F_std))
+                else:
+                    out.append((y[k] * n, F, None))
+                pos += 3 * nf
+        return out
 
     def add_structure(self, data, N_max=20, tol_e_var=1.2, tol_f_var=1.2, add_force=True):
         """

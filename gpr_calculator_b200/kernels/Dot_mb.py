@@ -64,8 +64,8 @@ class Dot_mb():
                               window=window, symmetric=symmetric)
         return K, None
 
-    def diag_device(self, data):
-        if "force" in data and isinstance(data["force"], tuple):
+    def diag_device(self, data, _packed_ok=False):
+        if "force" in data and isinstance(data["force"], tuple) and not _packed_ok:
             raise ValueError("Dot_mb.diag expects force data as a list of (x, dxdr, ele) (Dot_mb.py:71-78)")
         # the numpy K_ff behind Dot_mb.diag regularises every norm with +1e-8 (Dot_mb.py:206-221)
         e = energy_pack(data["energy"]) if "energy" in data else None

@@ -61,7 +61,7 @@ class RBF_mb():
         return k_total_device(_lib.RBF, float(self.sigma), float(self.l), float(self.zeta), side1, side2,
                               use_tol=not grad, tol=f_tol, grad=grad, window=window, symmetric=symmetric)
 
-    def diag_device(self, data):
+    def diag_device(self, data, _packed_ok=True):
         """Energy rows: eps-regularised formula of kernels/base.py:107-130; force rows: diagonal of
         the (I, I) block with kff_C's default tol = 1e-12 (RBF_mb.py:103-110)."""
         return diag_device(_lib.RBF, float(self.sigma), float(self.l), float(self.zeta), packs_of(data), tol=1e-12)

@@ -42,33 +42,19 @@ def packed_from_batch(des, atoms_list, centres_per_structure=None, chunk=64):
             (or the first `centres_per_structure` atoms of every structure), rows of a centre in
             increasing `seq` order exactly like argwhere(seq[:, 1] == i).
     """
-    ex, ee, ei, fx, fd, fe, fi = [], [], [], [], [], [], []
+    from .batch import rows_from_batch
+    Es, Fs = [], []
     for s0 in range(0, len(atoms_list), chunk):
         part = atoms_list[s0:s0 + chunk]
         r = des.calculate_batch(part, to_host=False)
-        x, dxdr, seq = r['x'], r['dxdr'], r['seq']
-        atom_ptr, seq_ptr, numbers = r['atom_ptr'].long(), r['seq_ptr'].long(), r['numbers']
-        A, Q = x.shape[0], seq.shape[0]
-        counts = atom_ptr[1:] - atom_ptr[:-1]
-        struct_of = torch.repeat_interleave(torch.arange(len(part), device=x.device), counts)
-        centre = torch.repeat_interleave(torch.arange(A, device=x.device), seq_ptr[1:] - seq_ptr[:-1])   # global centre of row q
-        gj = atom_ptr[struct_of[centre]] + seq[:, 1]                                                    # global force atom of row q
-        order = torch.sort(gj, stable=True).indices
-        n_rows = torch.bincount(gj, minlength=A)
+        centres = None
         if centres_per_structure is not None:
-            local = torch.arange(A, device=x.device) - atom_ptr[struct_of]
-            keep_atom = local < centres_per_structure
-            order = order[keep_atom[gj[order]]]
-            n_rows = n_rows[keep_atom]
-        fx.append(x[centre[order]])
-        fd.append(dxdr[order])
-        fe.append(numbers[centre[order]].to(torch.int32))
-        fi.append(n_rows.cpu())
-        ex.append(x)
-        ee.append(numbers.to(torch.int32))
-        ei.append(counts.cpu())
-    E = (torch.cat(ex), torch.cat(ee), [int(v) for v in torch.cat(ei)])
-    F = (torch.cat(fx), torch.cat(fd), torch.cat(fe), [int(v) for v in torch.cat(fi)])
+            centres = [range(min(centres_per_structure, len(a))) for a in part]
+        E, F = rows_from_batch(r, centres)
+        Es.append(E)
+        Fs.append(F)
+    E = (torch.cat([e[0] for e in Es]), torch.cat([e[1] for e in Es]), sum((e[2] for e in Es), []))
+    F = (torch.cat([f[0] for f in Fs]), torch.cat([f[1] for f in Fs]), torch.cat([f[2] for f in Fs]), sum((f[3] for f in Fs), []))
     return E, F
 
 

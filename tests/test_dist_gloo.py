@@ -30,6 +30,14 @@ def _worker(rank, size, port, q):
     local = torch.cat((full[e0:e1], full[NE + 3 * f0:NE + 3 * f1]))
     got = gd.gather_rows(local, windows, NE, N)
     ok = bool(torch.equal(got, full))
+    # in-place variant: every rank has written only its own slabs of the full matrix
+    mine = torch.full((N, N), -1.0, dtype=torch.float64)
+    mine[e0:e1] = full[e0:e1]
+    mine[NE + 3 * f0:NE + 3 * f1] = full[NE + 3 * f0:NE + 3 * f1]
+    gd.gather_rows_inplace(mine, windows, NE)
+    ok = ok and bool(torch.equal(mine, full))
+    wu = gd.row_windows([10] * NE, list(range(20, 20 + NF)), size, upper=True)
+    ok = ok and wu[0][1][0] == 0 and wu[-1][1][1] == NF and wu[0][1][1] <= windows[0][1][1]   # early rows cost more
     s = gd.all_reduce_sum([float(rank + 1), 2.0])
     q.put((rank, ok, s, gd.world()))
     dist.destroy_process_group()

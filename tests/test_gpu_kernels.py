@@ -178,6 +178,72 @@ def test_modes_and_windows_agree():
         assert (Kf - 1.3 ** 2 * K1).abs().max().item() <= 1e-13 * scale
 
 
+def test_upper_mode_windows_symmetrize_and_trace():
+    """The sharded build: every rank writes the J >= I blocks of its row window (FF_UPPER) into the full
+    matrix, gprb_symmetrize mirrors them; the upper-only gradient trace equals the full one."""
+    import ctypes
+    from gpr_calculator_b200 import _lib, dist as gd
+    from gpr_calculator_b200.device import Pack, k_total_device, build_force_rows, ptr, stream, c_vp
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(11)
+    X, dX, ELE, ind = list_to_tuple(make_force(rng, 37, lo=9, hi=41))
+    f = Pack(X, ELE, ind, dxdr=dX)
+    NF, N = 37, 3 * 37
+    Kref, dKref = k_total_device(_lib.RBF, 1.1, 0.6, 2.0, (None, f), None, use_tol=False, grad=True, symmetric=False)
+    for parts in (1, 2, 3):
+        windows = gd.row_windows([], ind, parts, upper=True)
+        assert windows[0][1][0] == 0 and windows[-1][1][1] == NF
+        K = torch.full((N, N), float("nan"), dtype=torch.float64, device="cuda")
+        dK = torch.full((N, N), float("nan"), dtype=torch.float64, device="cuda")
+        for (_, (f0, f1)) in windows:
+            build_force_rows(_lib.RBF, 1.1, 0.6, 2.0, (None, f), (None, f), (f0, f1), K[3 * f0:3 * f1], dK[3 * f0:3 * f1],
+                             use_tol=False, ff_mode=_lib.FF_UPPER)
+        up = torch.triu(torch.ones(N, N, dtype=torch.bool, device="cuda"))
+        assert (K - Kref)[up].abs().max().item() <= 1e-13 * Kref.abs().max().item()
+        _lib.call("gprb_symmetrize", ptr(K), N, N, stream())
+        assert (K - Kref).abs().max().item() <= 1e-13 * Kref.abs().max().item()
+        # trace of (alpha alpha^T - Kinv) dK over all rows: full rows vs upper-only rows
+        alpha = torch.randn(N, dtype=torch.float64, device="cuda")
+        Kinv = torch.randn(N, N, dtype=torch.float64, device="cuda")
+        Kinv = Kinv + Kinv.T
+        out_full, out_up = (ctypes.c_double * 2)(), (ctypes.c_double * 2)()
+        _lib.call("gprb_lml_grad_trace", N, 0, N, ptr(alpha), ptr(Kinv), N, ptr(dKref), N, 0, 0.3, 0.7, 0, out_full, stream())
+        _lib.call("gprb_lml_grad_trace", N, 0, N, ptr(alpha), ptr(Kinv), N, ptr(dK), N, 0, 0.3, 0.7, 1, out_up, stream())
+        want = 0.5 * ((torch.outer(alpha, alpha) - Kinv) * dKref).sum().item()
+        assert abs(out_full[0] - want) <= 1e-10 * abs(want) and abs(out_up[0] - want) <= 1e-10 * abs(want)
+        assert abs(out_full[1] - out_up[1]) <= 1e-12 * abs(out_full[1])
+
+
+def test_flat_tiles_share_groups():
+    """Groups that start and end in the middle of 8-row tiles and of 64-row CTA blocks on both sides,
+    empty groups, and a row window that starts inside a tile."""
+    from gpr_calculator_b200.kernels import rbf_kernel as rk
+    from gpr_calculator_b200 import _lib
+    from gpr_calculator_b200.device import Pack, k_total_device
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(12)
+    sizes1, sizes2 = [5, 1, 13, 64, 3, 97, 8, 7, 130, 2], [11, 96, 1, 1, 29, 63, 200, 5]
+    mk = lambda sizes: list_to_tuple([make_force(rng, 1, lo=n, hi=n)[0] for n in sizes])   # noqa: E731
+    F1, F2 = mk(sizes1), mk(sizes2)
+    from oracle import kernels as ok
+    O = ok.RBFOracle("port")
+    for grad in (False, True):
+        got, ref = rk.kff_C(F1, F2, 0.9, 0.8, 2.0, grad=grad), O.kff_C(F1, F2, 0.9, 0.8, 2.0, grad=grad)
+        got, ref = (got, ref) if grad else ((got,), (ref,))
+        for a, b in zip(got, ref):
+            assert rel_err(a, b) <= TOL
+    f1 = Pack(F1[0], F1[2], F1[3], dxdr=F1[1])
+    f2 = Pack(F2[0], F2[2], F2[3], dxdr=F2[1])
+    Kfull, _ = k_total_device(_lib.RBF, 0.9, 0.8, 2.0, (None, f1), (None, f2), use_tol=False)
+    Kwin, _ = k_total_device(_lib.RBF, 0.9, 0.8, 2.0, (None, f1), (None, f2), use_tol=False, window=((0, 0), (2, 7)))
+    assert torch.equal(Kwin, Kfull[6:21])
+    # an empty group yields zero rows / columns
+    Xe = np.concatenate((F1[0][:5], F1[0][5:]))
+    g = Pack(Xe, F1[2], [5, 0, 1, 13, 64, 3, 97, 8, 7, 130, 2], dxdr=F1[1])
+    Kg, _ = k_total_device(_lib.RBF, 0.9, 0.8, 2.0, (None, g), (None, f2), use_tol=False)
+    assert torch.count_nonzero(Kg[3:6]).item() == 0 and torch.equal(Kg[6:], Kfull[3:]) and torch.equal(Kg[:3], Kfull[:3])
+
+
 def test_kff_is_psd_and_deterministic():
     from gpr_calculator_b200 import _lib
     from gpr_calculator_b200.device import Pack, k_total_device
