@@ -194,6 +194,12 @@ class SimpleAtoms:
     def copy(self):
         return SimpleAtoms(self.numbers, self.positions, self.cell, self.pbc, self.constraints)
 
+    def get_potential_energy(self):
+        return self.calc.get_potential_energy(self)
+
+    def get_forces(self):
+        return self.calc.get_forces(self)
+
 
 class FixAtoms:
     """Stand-in for ase.constraints.FixAtoms (only get_indices is used, gaussianprocess.py:823-832)."""

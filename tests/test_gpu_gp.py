@@ -136,3 +136,47 @@ def test_add_structure_selection_and_refit(g):
     # predictions use only the fitted part of the training set while points wait in the queue
     E, F, _ = gp.predict_structure(at1, stress=False)
     assert np.isfinite(E) and np.all(np.isfinite(F))
+
+
+def test_gpr_calculator_adapter(capsys):
+    """GPR(base=..., ff=...) control flow (calculator.py:48-117): uncertain structures go to the base
+    calculator and enter the training queue, confident ones use the surrogate, the model is refitted
+    on the reference's cadence; result keys and printed lines as in the reference."""
+    from gpr_calculator_b200.calculator import GPR
+    from gpr_calculator_b200.gaussianprocess import GP
+    from gpr_calculator_b200.kernels import RBF_mb
+    from gpr_calculator_b200.SO3 import SO3
+    from gpr_calculator_b200.synthetic import cu_fcc, K_SPRING, A_CU
+
+    class Einstein:
+        """toy base calculator: harmonic wells on the fcc sites"""
+        def __init__(self):
+            self.site = cu_fcc(1, 0, noise=0.0)[0].positions
+        def get_potential_energy(self, atoms):
+            return 0.5 * K_SPRING * float(((atoms.positions - self.site) ** 2).sum())
+        def get_forces(self, atoms):
+            return -K_SPRING * (atoms.positions - self.site)
+
+    base = Einstein()
+    gp = GP(kernel=RBF_mb(para=[1.0, 0.5], zeta=2.0), descriptor=SO3(nmax=3, lmax=4, rcut=4.0),
+            noise_e=0.002, noise_f=0.05, log_file=None)
+    first = cu_fcc(1, 1, noise=0.08)[0]
+    first.calc = base
+    gp.add_structure((first.copy(), base.get_potential_energy(first), base.get_forces(first)))
+    with contextlib.redirect_stdout(io.StringIO()):
+        gp.fit(show=False)
+    calc = GPR(base=base, ff=gp, save=False, freq=2)
+    for k in range(2, 7):
+        at = cu_fcc(1, k, noise=0.08)[0]
+        calc.calculate(at)
+        assert set(("energy", "forces", "var_e", "var_f")) <= set(calc.results)
+        assert calc.results["forces"].shape == (4, 3) and np.isfinite(calc.results["energy"])
+    out = capsys.readouterr().out
+    assert "From Base model" in out or "From Surrogate" in out
+    assert gp.use_base + gp.use_surrogate == 5 and gp.use_base >= 1
+    assert gp.fits >= 2                      # at least one refit was triggered by the queue
+    assert calc.get_e(peratom=False) == calc.results["energy"] and calc.get_var_f().shape == (4, 3)
+    calc.freeze()
+    n_base = gp.use_base
+    calc.calculate(cu_fcc(1, 99, noise=0.3)[0])
+    assert gp.use_base == n_base             # frozen: the base calculator is not called
