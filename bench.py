@@ -49,6 +49,10 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes per launch of the K_ff(+grad) kernel, from ncu (13.28 GB read + 17.25 GB written at S5)
+KFF_DRAM_TRAFFIC = {"s5": 30.54e9}
+
+
 def flops_of(p_ff, p_ef, p_ee, d=D):
     return 32.0 * d * p_ff + 8.0 * d * p_ef + 2.0 * d * p_ee
 
@@ -285,7 +289,10 @@ def main():
     achieved = 32.0 * D * my_pff / (kff_ms_avg * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "kernel": "cov_mma_kernel<4,8,RBF,grad> (gprb_kff, FP64 DMMA.8x8x4)",
                 "achieved": achieved, "peak": float(peak[0]), "unit": "TFLOP/s", "frac": achieved / float(peak[0]),
-                "traffic": None, "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark (gprb_fp64_dmma_peak); "
+                "traffic": KFF_DRAM_TRAFFIC.get(args.workload) if world == 1 else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at this "
+                                  "size (profiles/r01_kff_s5_ncu_summary.txt); K and dK/dl written once = 17.05 GB",
+                "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark (gprb_fp64_dmma_peak); "
                 "MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 on this pool: 35.5 TFLOP/s",
                 "kff_ms_per_launch": kff_ms_avg, "algorithmic_flops_per_pair": 32 * D}
 

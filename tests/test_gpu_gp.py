@@ -173,8 +173,13 @@ def test_gpr_calculator_adapter(capsys):
         assert calc.results["forces"].shape == (4, 3) and np.isfinite(calc.results["energy"])
     out = capsys.readouterr().out
     assert "From Base model" in out or "From Surrogate" in out
-    assert gp.use_base + gp.use_surrogate == 5 and gp.use_base >= 1
-    assert gp.fits >= 2                      # at least one refit was triggered by the queue
+    assert gp.use_base + gp.use_surrogate == 5
+    calc.force_base = True                   # two labelled structures in the queue trigger a refit (calculator.py:102)
+    n_fits = gp.fits
+    for k in (50, 51):
+        calc.calculate(cu_fcc(1, k, noise=0.08)[0])
+    calc.force_base = False
+    assert gp.use_base >= 2 and gp.fits >= n_fits + 1 and gp.N_energy_queue < 2
     assert calc.get_e(peratom=False) == calc.results["energy"] and calc.get_var_f().shape == (4, 3)
     calc.freeze()
     n_base = gp.use_base

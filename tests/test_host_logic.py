@@ -128,3 +128,78 @@ def test_cur_selects_null_space_rows():
     K = np.outer(v, v) + np.diag([0.0, 0.0, 1.0])     # rows 0 and 1 are redundant
     ids = CUR(K, 1e-10)
     assert len(ids) == 1 and ids[0] in (0, 1)
+
+
+def test_gpr_adapter_gate_and_refit_cadence(capsys):
+    """GPR.calculate control flow with a scripted surrogate (no GPU): uncertainty gate
+    (calculator.py:62-73), base fall-back + add_structure, refit trigger (:101-103), freeze()."""
+    import numpy as np
+    from gpr_calculator_b200.calculator import GPR
+    from gpr_calculator_b200.utilities import SimpleAtoms, FixAtoms
+
+    class FakeGP:
+        noise_e, noise_f = 0.002, 0.1
+        use_base = use_surrogate = fits = 0
+        N_forces = N_queue = N_energy_queue = 0
+        error = {"energy_mae": 0.0, "forces_mae": 0.0}
+        f_std = 0.01
+
+        def predict_structure(self, atoms, stress, return_std, f_tol=1e-12):
+            n = len(atoms)
+            return 1.0, np.full((n, 3), 0.05), None, 0.001, np.full((n, 3), self.f_std)
+
+        def add_structure(self, data):
+            self.N_queue += 3
+            self.N_energy_queue += 1
+
+        def fit(self, opt=True, show=False, maxiter=10):
+            self.fits += 1
+            self.N_queue = self.N_energy_queue = 0
+
+        def validate_data(self, show=False):
+            pass
+
+    class Base:
+        def get_potential_energy(self, atoms):
+            return -7.0
+
+        def get_forces(self, atoms):
+            return np.ones((len(atoms), 3))
+
+    at = SimpleAtoms([13, 13, 79], np.zeros((3, 3)), np.eye(3) * 5, constraints=[FixAtoms([0])])
+    gp = FakeGP()
+    calc = GPR(base=Base(), ff=gp, save=False, freq=10)
+    calc.calculate(at)                                    # F_std 0.01 < max(0.12, 0.05/2.5): surrogate
+    assert gp.use_surrogate == 1 and gp.use_base == 0 and calc.results["energy"] == 1.0
+    gp.f_std = 0.5                                        # above the gate: base calculator, labels replace the prediction
+    calc.calculate(at)
+    assert gp.use_base == 1 and calc.results["energy"] == -7.0
+    assert np.all(calc.results["forces"][0] == 0.0) and np.all(calc.results["forces"][1:] == 1.0)   # FixAtoms rows zeroed
+    assert gp.fits == 0 and gp.N_energy_queue == 1
+    calc.calculate(at)                                    # second queued energy triggers the refit (N_energy_queue >= 2)
+    assert gp.use_base == 2 and gp.fits == 1 and gp.N_queue == 0
+    calc.freeze()
+    calc.calculate(at)
+    assert gp.use_base == 2 and gp.use_surrogate == 2     # frozen: never calls the base
+    out = capsys.readouterr().out
+    assert out.count("From Base model") == 2 and out.count("From Surrogate") == 2
+    assert calc.get_var_f().shape == (3, 3) and calc.get_e() == calc.results["energy"] / 3
+
+
+def test_synthetic_pair_counts_and_windows():
+    import numpy as np
+    from gpr_calculator_b200.synthetic import pair_counts, cu_fcc
+    from gpr_calculator_b200 import dist as gd
+    ele = np.array([29] * 5 + [13] * 3 + [29] * 2)
+    ind = [4, 4, 2]                                       # groups: 4x29 | 29,13,13,13 | 29,29
+    full = pair_counts(ele, ind, symmetric=False)
+    assert full == 7 * 7 + 3 * 3
+    up = pair_counts(ele, ind, symmetric=True)
+    brute = sum((ele[a] == ele[b]) for I in range(3) for J in range(I, 3)
+                for a in range(sum(ind[:I]), sum(ind[:I + 1])) for b in range(sum(ind[:J]), sum(ind[:J + 1])))
+    assert up == brute
+    at, E, F = cu_fcc(2, 7)
+    assert len(at) == 32 and F.shape == (32, 3) and E > 0
+    w = gd.row_windows([32] * 7, [28] * 40, 4, upper=True)
+    sizes = [f1 - f0 for _, (f0, f1) in w]
+    assert sum(sizes) == 40 and sizes[0] < sizes[-1]      # early rows carry longer sweeps
