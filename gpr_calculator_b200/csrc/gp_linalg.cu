@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include <cusolverDn.h>
 #include <cublas_v2.h>
+#include <cstdlib>
 
 namespace {
 
@@ -210,11 +211,38 @@ extern "C" int gprb_chol_solve_vec(const double *L, long long ldl, int N, double
     return GPRB_OK;
 }
 
+__global__ void set_identity_kernel(double *A, long long ld, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) A[(long long)i * ld + i] = 1.0;
+}
+
 extern "C" int gprb_chol_inverse(const double *L, long long ldl, int N, double *Kinv, long long ldi, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(L && Kinv && N > 0, "gprb_chol_inverse: bad argument");
     int rc = handles(st);
     if (rc) return rc;
+    if ((long long)N * N >= (1LL << 31) || getenv("GPRB_FORCE_TRSM") != nullptr) {   // env: test hook for the large-N route
+        // cuSOLVER's potri (and the 64-bit trtri) reject N^2 >= 2^31 (N > 46340, e.g. the S4 configuration).
+        // Same result the way gaussianprocess.py:195 gets it, cho_solve(L, I): two triangular solves with
+        // the 64-bit cuBLAS interface on an identity right-hand side held in the output buffer.
+        dim3 grid((N + 31) / 32, (N + 31) / 32), block(32, 32);
+        GPRB_CUDA(cudaMemset2DAsync(Kinv, ldi * sizeof(double), 0, (size_t)N * sizeof(double), N, st));
+        set_identity_kernel<<<(N + 255) / 256, 256, 0, st>>>(Kinv, ldi, N);
+        GPRB_LAUNCHED();
+        const double one = 1.0;
+        // column-major view: K = U^T U with U in the upper triangle of L's buffer;  U^T Y = I, then U X = Y
+        cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+                                           (int64_t)N, (int64_t)N, &one, L, (int64_t)ldl, Kinv, (int64_t)ldi);
+        cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+                                           (int64_t)N, (int64_t)N, &one, L, (int64_t)ldl, Kinv, (int64_t)ldi);
+        if (b1 != CUBLAS_STATUS_SUCCESS || b2 != CUBLAS_STATUS_SUCCESS) {
+            gprb_set_error("cublasDtrsm_64 status %d / %d", (int)b1, (int)b2); return GPRB_ERR_CUDA;
+        }
+        mirror_lower_kernel<<<grid, block, 0, st>>>(Kinv, ldi, N);     // exactly symmetric, like the potri route
+        GPRB_LAUNCHED();
+        GPRB_CUDA(cudaGetLastError());
+        return GPRB_OK;
+    }
     GPRB_CUDA(cudaMemcpy2DAsync(Kinv, ldi * sizeof(double), L, ldl * sizeof(double), (size_t)N * sizeof(double), N,
                                 cudaMemcpyDeviceToDevice, st));
     int lwork = 0;

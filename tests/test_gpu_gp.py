@@ -185,3 +185,27 @@ def test_gpr_calculator_adapter(capsys):
     n_base = gp.use_base
     calc.calculate(cu_fcc(1, 99, noise=0.3)[0])
     assert gp.use_base == n_base             # frozen: the base calculator is not called
+
+
+def test_inverse_large_n_route_matches_potri(monkeypatch):
+    """gprb_chol_inverse switches from potri to two 64-bit triangular solves when N^2 >= 2^31 (S4: N = 65000); the test hook
+    forces that route at a small size and compares both against numpy."""
+    import torch
+    from gpr_calculator_b200 import _lib
+    from gpr_calculator_b200.device import ptr, stream
+    rng = np.random.default_rng(3)
+    N = 300
+    A = rng.normal(size=(N, N))
+    K = A @ A.T + N * np.eye(N)
+    Kd = torch.as_tensor(K, device="cuda").contiguous()
+    _lib.call("gprb_chol_factor", ptr(Kd), N, N, stream())
+    outs = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("GPRB_FORCE_TRSM", "1")
+        Kinv = torch.empty((N, N), dtype=torch.float64, device="cuda")
+        _lib.call("gprb_chol_inverse", ptr(Kd), N, N, ptr(Kinv), N, stream())
+        outs.append(Kinv.cpu().numpy())
+    ref = np.linalg.inv(K)
+    for o in outs:
+        assert rel_err(o, ref) <= 1e-10 and np.abs(o - o.T).max() == 0.0
