@@ -8,8 +8,8 @@ c_nlm / grad c_nlm and the power spectrum with its derivative are computed by li
 
 ``calculate_batch`` processes many structures in one pass and can leave the results on device
 (what the batched prediction benchmark uses).  Only the cosine cut-off exists in the reference
-(the other names at SO3.py:157-170 are undefined there); stress (`rdxdr`) is not part of the hot
-path yet.
+(the other names at SO3.py:157-170 are undefined there).  stress=True also returns
+``rdxdr[n_seq, d, 3, 3] = -pstress / volume`` (SO3.py:253-273, 304-306).
 """
 import ctypes
 
@@ -224,8 +224,8 @@ class SO3:
         ``{'x' [A,d], 'dxdr' [Q,d,3], 'seq' [Q,2] (local atom ids), 'atom_ptr', 'seq_ptr', 'numbers'}``.
         """
         require_cuda()
-        if self.stress:
-            raise NotImplementedError("SO3(stress=True) (rdxdr) is not part of the B200 hot path yet (SURVEY.md §8f)")
+        if self.stress and not self.derivative:
+            raise ValueError("stress=True needs derivative=True")
         if self.lmax > 15:
             raise NotImplementedError("the device kernels support lmax <= 15")
         S = len(structures)
@@ -267,17 +267,23 @@ class SO3:
         x = torch.zeros((A, d), dtype=torch.float64, device="cuda")
         dxdr = torch.zeros((n_seq, d, 3), dtype=torch.float64, device="cuda") if self.derivative else None
         seq = torch.zeros((n_seq, 2), dtype=torch.int64, device="cuda") if self.derivative else None
+        rdxdr = inv_vol = None
+        if self.stress:
+            # rdxdr = -pstress / volume (SO3.py:304-306)
+            rdxdr = torch.zeros((n_seq, d, 3, 3), dtype=torch.float64, device="cuda")
+            inv_vol = dev(1.0 / np.abs(np.linalg.det(cells.reshape(S, 3, 3))), torch.float64)
         _lib.call("gprb_so3_power", A, ptr(nb_ptr), ptr(nb_j), ptr(nb_rvec), ptr(rad), ptr(t_num), ptr(t_atom_ptr),
                   ptr(t_struct_of), ptr(seq_ptr), self.nmax, self.lmax, float(self.alpha), float(self.rcut), ptr(norm),
-                  1 if self.derivative else 0, ptr(x), ptr(dxdr), ptr(seq), st)
+                  1 if self.derivative else 0, ptr(x), ptr(dxdr), ptr(seq), ptr(t_pos), ptr(inv_vol), ptr(rdxdr), st)
         if not to_host:
-            return {'x': x, 'dxdr': dxdr, 'seq': seq, 'atom_ptr': t_atom_ptr, 'seq_ptr': seq_ptr, 'numbers': t_num,
-                    'n_neighbors': n_nb}
+            return {'x': x, 'dxdr': dxdr, 'rdxdr': rdxdr, 'seq': seq, 'atom_ptr': t_atom_ptr, 'seq_ptr': seq_ptr,
+                    'numbers': t_num, 'n_neighbors': n_nb}
         xh = x.cpu().numpy()
         out = []
         if self.derivative:
             dh, sh = dxdr.cpu().numpy(), seq.cpu().numpy()
             seq_atom = seq_ptr.cpu().numpy()
+            rh_ = rdxdr.cpu().numpy() if rdxdr is not None else None
         for k, s in enumerate(structures):
             a0, a1 = int(atom_ptr[k]), int(atom_ptr[k + 1])
             item = {'x': xh[a0:a1], 'dxdr': None, 'rdxdr': None, 'elements': list(s.symbols)}
@@ -285,6 +291,8 @@ class SO3:
                 q0, q1 = int(seq_atom[a0]), int(seq_atom[a1])
                 item['dxdr'] = dh[q0:q1]
                 item['seq'] = sh[q0:q1]
+                if rh_ is not None:
+                    item['rdxdr'] = rh_[q0:q1]
             out.append(item)
         return out
 

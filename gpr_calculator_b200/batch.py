@@ -8,12 +8,14 @@ seq[:, 1] == i, in increasing row order (gaussianprocess.py:857-861, utilities.p
 import torch
 
 
-def rows_from_batch(r, centres=None):
+def rows_from_batch(r, centres=None, stress=False):
     """r: dict returned by SO3.calculate_batch(..., to_host=False).
 
     centres: None (every atom is a force centre) or a list with, per structure, the local atom ids to
     keep (e.g. the atoms not held by FixAtoms), in increasing order.
-    Returns (energy tuple (X [A,d], ELE [A], indices [S]), force tuple (X [R,d], dXdR [R,d,3], ELE [R],
+    stress=True appends the 6 Voigt columns of rdxdr (xx, yy, zz, xy, xz, yz — gaussianprocess.py:862-864) to
+    dXdR (9 columns; the descriptor must have been created with stress=True).
+    Returns (energy tuple (X [A,d], ELE [A], indices [S]), force tuple (X [R,d], dXdR [R,d,3 or 9], ELE [R],
     indices [NF]) or None when no force centre is kept); tensors live on the device.
     """
     x, dxdr, seq = r['x'], r['dxdr'], r['seq']
@@ -39,5 +41,11 @@ def rows_from_batch(r, centres=None):
         order = order[keep[gj[order]]]
         n_rows = n_rows[keep]
     cen = centre[order]
-    F = (x[cen], dxdr[order], numbers[cen].to(torch.int32), [int(v) for v in n_rows.cpu()])
+    dX = dxdr[order]
+    if stress:
+        if r.get('rdxdr') is None:
+            raise ValueError("stress rows need a descriptor created with stress=True (rdxdr)")
+        voigt = r['rdxdr'][order].reshape(dX.shape[0], dX.shape[1], 9)[:, :, [0, 4, 8, 1, 2, 5]]
+        dX = torch.cat((dX, voigt), dim=2)
+    F = (x[cen], dX, numbers[cen].to(torch.int32), [int(v) for v in n_rows.cpu()])
     return E, F

@@ -211,6 +211,7 @@ struct SO3Power {
     const int *numbers; const int *atom_ptr; const int *struct_of; const int *seq_ptr;
     double *x; double *dxdr; long long *seq;
     int derivative;
+    const double *pos; const double *inv_vol; double *rdxdr;   // stress: rdxdr[n_seq][d][3][3] = -pstress / volume
 };
 
 // one CTA per centre atom
@@ -225,6 +226,10 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
     double *sAcc = reinterpret_cast<double *>(sY + (LY + 1) * (LY + 1));            // [d*3] current j group
     double *sSelf = sAcc + 3 * d;                                                   // [d*3] sum over j != i
     double *sGeo = sSelf + 3 * d;                                                   // [16] per-neighbour scalars
+    double *sAccR = sGeo + 16;                                                      // [d*9] R_j (x) dP of the current j group
+    double *sSelfR = sAccR + 9 * d;                                                 // [d*9] the j == i group (own images)
+    double *sTot = sSelfR + 9 * d;                                                  // [d*3] sum of dP over all neighbours
+    const bool stress = a.rdxdr != nullptr;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int i = blockIdx.x;
     const int w0 = a.nb_ptr[i], w1 = a.nb_ptr[i + 1];
@@ -233,6 +238,10 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
 
     for (int e = tid; e < nent; e += nt) sC[e] = make_cuDoubleComplex(0.0, 0.0);
     for (int o = tid; o < 3 * d; o += nt) { sAcc[o] = 0.0; sSelf[o] = 0.0; }
+    if (stress) {
+        for (int o = tid; o < 9 * d; o += nt) { sAccR[o] = 0.0; sSelfR[o] = 0.0; }
+        for (int o = tid; o < 3 * d; o += nt) sTot[o] = 0.0;
+    }
     __syncthreads();
 
     auto geometry = [&](int w) {
@@ -370,8 +379,15 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
                 s += d1.x * c2.x + d1.y * c2.y + d2.x * c1.x + d2.y * c1.y;
             }
             sAcc[o] += s;
+            if (stress) {      // pstress[(i,j)] -= R_j (x) dP(w), R_j = r_i + r_ij (SO3.py:226, 254, 264)
+                sTot[o] += s;
+#pragma unroll
+                for (int n3 = 0; n3 < 3; n3++)
+                    sAccR[(pl * 3 + n3) * 3 + k] += (a.pos[3 * (size_t)i + n3] + a.nb_rvec[3 * (size_t)w + n3]) * s;
+            }
         }
         // flush when the next neighbour belongs to another atom
+        if (stress) __syncthreads();      // the 9-column accumulators are re-partitioned over the threads below
         const int j = a.nb_j[w];
         const bool last_of_j = (w + 1 == w1) || (a.nb_j[w + 1] != j);
         if (last_of_j) {
@@ -379,6 +395,7 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
             if (j == i) {
                 self_row = row++; self_done = true;
                 for (int o = tid; o < 3 * d; o += nt) sAcc[o] = 0.0;     // own images cancel (SO3.py:267-273)
+                if (stress) for (int o = tid; o < 9 * d; o += nt) { sSelfR[o] = sAccR[o]; sAccR[o] = 0.0; }
             } else {
                 const int rj = row++;
                 for (int o = tid; o < 3 * d; o += nt) {
@@ -387,12 +404,24 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
                     sSelf[o] += v;
                     sAcc[o] = 0.0;
                 }
+                if (stress) {
+                    const double iv = a.inv_vol[a.struct_of[i]];
+                    for (int o = tid; o < 9 * d; o += nt) { a.rdxdr[(size_t)rj * 9 * d + o] = sAccR[o] * iv; sAccR[o] = 0.0; }
+                }
                 if (tid == 0) { a.seq[2 * (size_t)rj] = i - a0; a.seq[2 * (size_t)rj + 1] = j - a0; }
             }
         }
     }
     if (!self_done) self_row = row++;
     for (int o = tid; o < 3 * d; o += nt) a.dxdr[(size_t)self_row * 3 * d + o] = -sSelf[o];
+    if (stress) {      // pstress[(i,i)] = -sum_{own images} R_j (x) dP + R_i (x) sum_w dP ; rdxdr = -pstress / vol
+        __syncthreads();
+        const double iv = a.inv_vol[a.struct_of[i]];
+        for (int o = tid; o < 9 * d; o += nt) {
+            const int k = o % 3, n3 = (o / 3) % 3, pl = o / 9;
+            a.rdxdr[(size_t)self_row * 9 * d + o] = (sSelfR[o] - a.pos[3 * (size_t)i + n3] * sTot[pl * 3 + k]) * iv;
+        }
+    }
     if (tid == 0) { a.seq[2 * (size_t)self_row] = i - a0; a.seq[2 * (size_t)self_row + 1] = i - a0; }
 }
 
@@ -432,16 +461,18 @@ extern "C" int gprb_so3_radial(int n_nb, const double *nb_rvec, int nmax, int lm
 extern "C" int gprb_so3_power(int n_atoms, const int *nb_ptr, const int *nb_j, const double *nb_rvec, const double *rad,
                               const int *numbers, const int *atom_ptr, const int *struct_of, const int *seq_ptr,
                               int nmax, int lmax, double alpha, double rcut, const double *norm_l, int derivative,
-                              double *x, double *dxdr, long long *seq, void *stream) {
+                              double *x, double *dxdr, long long *seq,
+                              const double *pos, const double *inv_vol, double *rdxdr, void *stream) {
     if (n_atoms == 0) return GPRB_OK;
     GPRB_REQUIRE(nb_ptr && numbers && atom_ptr && struct_of && norm_l && x, "gprb_so3_power: NULL argument");
     GPRB_REQUIRE(!derivative || (seq_ptr && dxdr && seq), "gprb_so3_power: derivative outputs missing");
     GPRB_REQUIRE(nmax >= 1 && lmax >= 0 && lmax <= SO3_MAXL - 1, "gprb_so3_power: need nmax >= 1 and 0 <= lmax <= %d", SO3_MAXL - 1);
     SO3Params p{nmax, lmax, 0, alpha, rcut, nullptr, nullptr, norm_l};
-    SO3Power a{nb_ptr, nb_j, nb_rvec, rad, numbers, atom_ptr, struct_of, seq_ptr, x, dxdr, seq, derivative};
+    GPRB_REQUIRE(!rdxdr || (derivative && pos && inv_vol), "gprb_so3_power: stress output needs derivative, pos and inv_vol");
+    SO3Power a{nb_ptr, nb_j, nb_rvec, rad, numbers, atom_ptr, struct_of, seq_ptr, x, dxdr, seq, derivative, pos, inv_vol, rdxdr};
     const int L1 = lmax + 1, M = 2 * lmax + 1, LY = lmax + 1;
     const int nent = nmax * L1 * M, d = nmax * (nmax + 1) / 2 * L1;
-    const size_t smem = (size_t)(4 * nent + (LY + 1) * (LY + 1)) * sizeof(cuDoubleComplex) + (size_t)(6 * d + 16) * sizeof(double);
+    const size_t smem = (size_t)(4 * nent + (LY + 1) * (LY + 1)) * sizeof(cuDoubleComplex) + (size_t)(6 * d + 16 + 21 * d) * sizeof(double);
     GPRB_REQUIRE(smem <= 200 * 1024, "gprb_so3_power: nmax=%d lmax=%d needs %zu bytes of shared memory", nmax, lmax, smem);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {

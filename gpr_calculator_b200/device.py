@@ -169,6 +169,51 @@ def force_pack(data, norm_eps=0.0):
     return Pack(X, ELE, indices, dxdr=dXdR, norm_eps=norm_eps)
 
 
+def stress_packs(data):
+    """Force data whose dxdr carries 9 columns (3 force + 6 Voigt stress columns, gaussianprocess.py:862-864)
+    -> (force Pack, stress Pack of columns 3:6, stress Pack of columns 6:9).  The Voigt columns enter the
+    algebra exactly like force columns (rbf_kernel.cpp:642-822), so each triple is packed as a force side."""
+    if isinstance(data, tuple) and len(data) == 3 and all(isinstance(p, Pack) for p in data):
+        return data                                   # already split
+    if not isinstance(data, tuple):
+        from .utilities import list_to_tuple
+        data = list_to_tuple(list(data), stress=True)
+    X, dXdR, ELE, indices = data
+    if dXdR.shape[2] != 9:
+        raise ValueError("stress data needs dxdr with 9 columns, got %d" % dXdR.shape[2])
+    cols = lambda a, b: dXdR[:, :, a:b] if isinstance(dXdR, torch.Tensor) else np.ascontiguousarray(dXdR[:, :, a:b])  # noqa: E731
+    return tuple(Pack(X, ELE, indices, dxdr=cols(a, a + 3)) for a in (0, 3, 6))
+
+
+def interleave_stress(Ka, Kb, n_groups):
+    """[3 G, n] rows of the two stress triples -> [6 G, n] with rows (group, voigt 0..5)."""
+    n = Ka.shape[1]
+    return torch.cat((Ka.reshape(n_groups, 3, n), Kb.reshape(n_groups, 3, n)), dim=1).reshape(6 * n_groups, n)
+
+
+def k_total_stress_device(kernel, p0, p1, zeta, data1, data2, use_tol=True, tol=1e-10, zeta_ef=None, zeta_ff=None):
+    """(K [NE1 + 3 NF1, N2], K1 [6 NF1, N2]) between a test side whose force data carry the stress columns and a
+    training side (k_total_with_stress, RBF_mb.py:206-229 / Dot_mb.py:150-173)."""
+    require_cuda()
+    e1 = energy_pack(data1["energy"]) if "energy" in data1 else None
+    f1 = sa = sb = None
+    if "force" in data1 and len(data1["force"]) > 0:
+        f1, sa, sb = stress_packs(data1["force"])
+    side2 = packs_of(data2)
+    K, _ = k_total_device(kernel, p0, p1, zeta, (e1, f1), side2, use_tol=use_tol, tol=tol, grad=False,
+                          zeta_ef=zeta_ef, zeta_ff=zeta_ff)
+    if f1 is None:
+        return K, None
+    NF1, n_cols = f1.n_groups, K.shape[1]
+    parts = []
+    for spack in (sa, sb):
+        Ks = torch.empty((3 * NF1, n_cols), dtype=F64, device="cuda")
+        build_force_rows(kernel, p0, p1, zeta, (None, spack), side2, (0, NF1), Ks, None, use_tol=use_tol, tol=tol,
+                         zeta_ef=zeta_ef, zeta_ff=zeta_ff, ff_mode=_lib.FF_FULL)
+        parts.append(Ks)
+    return K, interleave_stress(parts[0], parts[1], NF1)
+
+
 def packs_of(data):
     """dict {'energy':…, 'force':…} -> (energy Pack or None, force Pack or None)."""
     e = energy_pack(data["energy"]) if "energy" in data else None

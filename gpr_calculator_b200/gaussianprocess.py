@@ -389,10 +389,15 @@ class GP():
         Predict energy/force rows for packed or listed data `X` (gaussianprocess.py:319-379).
         """
         require_cuda()
-        if stress:
-            raise NotImplementedError("stress prediction is not part of the B200 hot path yet (SURVEY.md §8f)")
         train_x = self.get_train_x()
-        K_trans, mean, var = self._predict_device(X, train_x, 1e-10, return_std and not return_cov)
+        if stress:
+            # gaussianprocess.py:331-333: K* from k_total_with_stress, the stress rows themselves are discarded
+            K_trans, _ = self.kernel.k_total_stress_device(X, train_x)
+            return_std = return_cov = False
+            mean = K_trans @ self._alpha_dev
+            var = None
+        else:
+            K_trans, mean, var = self._predict_device(X, train_x, 1e-10, return_std and not return_cov)
         y_mean = mean.cpu().numpy()
 
         Npts = 0
@@ -667,14 +672,14 @@ class GP():
         """
         Energy, forces (and their standard deviations) of one structure (:834-918).
 
-        Note: the reference's default stress=True needs the stress covariance blocks, which are
-        not part of the B200 hot path yet; pass stress=False (what GPR.calculate does by default,
-        calculator.py:124-127).
+        stress=True (the reference's default) needs a descriptor created with stress=True; every atom is
+        then a force centre (gaussianprocess.py:862-864) and S is the per-atom stress [n_atoms, 6] in the
+        order xx, yy, zz, xy, xz, yz (:890-891).  GPR.calculate passes stress=False by default
+        (calculator.py:124-127).
         """
         require_cuda()
         if stress:
-            raise NotImplementedError("stress prediction is not part of the B200 hot path yet (SURVEY.md §8f); "
-                                      "call predict_structure(struc, stress=False, ...)")
+            return self._predict_structure_stress(struc, return_std, f_tol)
         fix_ids = set(self._get_fixed_atoms(struc))
         free_ids = [i for i in range(len(struc)) if i not in fix_ids]
         if hasattr(self.descriptor, "calculate_batch"):
@@ -711,6 +716,50 @@ class GP():
             F_std = np.zeros((len(struc), 3))
             F_std[free_ids] = y_std[1:].reshape([len(free_ids), 3])
             return E, F, S, E_std, F_std
+        return E, F, S
+
+    def _predict_structure_stress(self, struc, return_std, f_tol):
+        """predict_structure(stress=True): K* rows of the energy, of all 3 n force components and of the
+        6 n Voigt stress components (k_total_with_stress), mean = K* alpha."""
+        from .batch import rows_from_batch
+        from .device import energy_pack, stress_packs
+        if not getattr(self.descriptor, "stress", False) or not hasattr(self.descriptor, "calculate_batch"):
+            raise ValueError("predict_structure(stress=True) needs a descriptor created with stress=True "
+                             "(the reference reads d['rdxdr'], gaussianprocess.py:862)")
+        n = len(struc)
+        fixed = set(self._get_fixed_atoms(struc))
+        free_ids = [i for i in range(n) if i not in fixed]
+        E_t, F_t = rows_from_batch(self.descriptor.calculate_batch([struc], to_host=False), None, stress=True)
+        e1, (f1, sa, sb) = energy_pack(E_t), stress_packs(F_t)
+        train_x = self.get_train_x()
+        K, K1 = self.kernel.k_total_stress_device({"energy": e1, "force": (f1, sa, sb)}, train_x, tol=f_tol)
+        m, N = K.shape
+        mean = torch.empty(m, dtype=F64, device="cuda")
+        var = diag = work = None
+        if return_std:
+            diag = self.kernel.diag_device({"energy": E_t, "force": (F_t[0], F_t[1][:, :, :3].contiguous(), F_t[2], F_t[3])}
+                                           if isinstance(self.kernel, Dot_mb) else {"energy": e1, "force": f1}, _packed_ok=True)
+            var = torch.empty(m, dtype=F64, device="cuda")
+            work = torch.empty((m, N), dtype=F64, device="cuda")
+            self.set_K_inv()
+        _lib.call("gprb_predict", m, N, ptr(K), N, ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
+                  ptr(diag), ptr(mean), ptr(var), ptr(work), stream())
+        y_mean = mean.cpu().numpy()
+        E = y_mean[0] * n
+        F_all = y_mean[1:].reshape(n, 3)
+        F = np.zeros((n, 3))
+        F[free_ids] = F_all[free_ids]
+        S = (K1 @ self._alpha_dev).cpu().numpy().reshape(n, 6)
+        if self.base_potential is not None:
+            energy_off, force_off, stress_off = self.compute_base_potential(struc)
+            E += energy_off
+            F += force_off
+            S += stress_off
+        if return_std:
+            y_std = np.sqrt(var.cpu().numpy())
+            F_std = np.zeros((n, 3))
+            F_std[free_ids] = y_std[1:].reshape(n, 3)[free_ids]
+            return E, F, S, y_std[0], F_std
         return E, F, S
 
     def predict_structures(self, strucs, return_std=False, f_tol=1e-8, batch=32):

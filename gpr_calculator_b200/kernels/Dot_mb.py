@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..device import packs_of, k_total_device, diag_device, energy_pack, force_pack
+from ..device import packs_of, k_total_device, k_total_stress_device, diag_device, energy_pack, force_pack
 
 
 class Dot_mb():
@@ -88,5 +88,12 @@ class Dot_mb():
         C2[:NE, :NE] = 0.8 * 2 * self.sigma ** 2 * self.sigma0
         return K, np.dstack((2 * K / self.sigma, C2))
 
+    def k_total_stress_device(self, data1, data2, tol=1e-10):
+        # same zeta-in-the-sigma0-slot quirk as k_total: the cross blocks use zeta = 2 (Dot_mb.py:166-170)
+        return k_total_stress_device(_lib.DOT, float(self.sigma), float(self.sigma0), float(self.zeta), data1, data2,
+                                     use_tol=False, tol=0.0, zeta_ef=2.0, zeta_ff=2.0)
+
     def k_total_with_stress(self, data1, data2, tol=1e-10):
-        raise NotImplementedError("stress blocks are not part of the B200 hot path yet (SURVEY.md §8f)")
+        """Dot_mb.py:150-173 (tol is not used there either)."""
+        K, K1 = self.k_total_stress_device(data1, data2)
+        return K.cpu().numpy(), (None if K1 is None else K1.cpu().numpy())

@@ -11,7 +11,7 @@ GP.predict use so that K never leaves HBM).  The reference's mpi4py row split
 import numpy as np
 
 from .. import _lib
-from ..device import packs_of, k_total_device, diag_device
+from ..device import packs_of, k_total_device, k_total_stress_device, diag_device
 
 
 class RBF_mb():
@@ -82,6 +82,13 @@ class RBF_mb():
         K = K.cpu().numpy()
         return K, np.dstack(((2 / self.sigma) * K, dK_l.cpu().numpy()))
 
+    def k_total_stress_device(self, data1, data2, tol=1e-10):
+        """(K, K1) as CUDA tensors; K1 holds the 6 Voigt stress rows of every force item of data1."""
+        return k_total_stress_device(_lib.RBF, float(self.sigma), float(self.l), float(self.zeta), data1, data2,
+                                     use_tol=True, tol=tol)
+
     def k_total_with_stress(self, data1, data2, tol=1e-10):
-        raise NotImplementedError("stress blocks are not part of the B200 hot path yet (SURVEY.md §8f; "
-                                  "the reference marks this path obsolete, RBF_mb.py:210)")
+        """Covariance for energy / force / stress prediction (RBF_mb.py:206-229): data1's force items carry
+        9 columns (3 force + 6 Voigt).  Returns (C, C1) with C1 = [C_se, C_sf]."""
+        K, K1 = self.k_total_stress_device(data1, data2, tol=tol)
+        return K.cpu().numpy(), (None if K1 is None else K1.cpu().numpy())

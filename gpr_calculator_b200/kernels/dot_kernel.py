@@ -2,7 +2,7 @@
 import numpy as np
 
 from .. import _lib
-from ..device import energy_pack, force_pack, empty, ptr, stream, require_cuda, c_vp
+from ..device import energy_pack, force_pack, stress_packs, interleave_stress, empty, ptr, stream, require_cuda, c_vp
 
 
 def _host(t):
@@ -25,8 +25,18 @@ def kee_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False):
 def kef_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False, transpose=False):
     """dot_kernel.py:66-160 (sigma0 does not enter; d/dsigma0 = 0, :154)."""
     require_cuda()
-    if stress:
-        raise NotImplementedError("stress blocks are not part of the B200 hot path yet (SURVEY.md §8f)")
+    if stress:     # dot_kef_many_stress (dot_kernel.cpp:133-216): C [m1, 3 m2], C_s [m1, 6 m2]
+        e = energy_pack(X1)
+        packs = stress_packs(X2)
+        blocks = []
+        for f in packs:
+            K = empty(e.n_groups, 3 * f.n_groups)
+            _lib.call("gprb_kef", _lib.DOT, e.handle, f.handle, float(sigma), float(sigma0), float(zeta), 0, f.n_groups,
+                      ptr(K), 3 * f.n_groups, c_vp(0), 0, c_vp(0), 0, c_vp(0), 0, stream())
+            blocks.append(K)
+        Cs = interleave_stress(blocks[1].T.contiguous(), blocks[2].T.contiguous(), packs[0].n_groups).T
+        C, Cs = _host(blocks[0]), _host(Cs.contiguous())
+        return (C.T, Cs.T) if transpose else (C, Cs)
     e, f = energy_pack(X1), force_pack(X2)
     K = empty(e.n_groups, 3 * f.n_groups)
     _lib.call("gprb_kef", _lib.DOT, e.handle, f.handle, float(sigma), float(sigma0), float(zeta), 0, f.n_groups,
@@ -42,8 +52,16 @@ def kef_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False, tra
 def kff_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False):
     """dot_kernel.py:162-270 (no pair cut; d/dsigma0 = 0, :265)."""
     require_cuda()
-    if stress:
-        raise NotImplementedError("stress blocks are not part of the B200 hot path yet (SURVEY.md §8f)")
+    if stress:     # dot_kff_many_stress (dot_kernel.cpp:338-508): C [3 m1, 3 m2], C_s [6 m1, 3 m2]
+        packs = stress_packs(X1)
+        f2 = force_pack(X2)
+        blocks = []
+        for f1 in packs:
+            K = empty(3 * f1.n_groups, 3 * f2.n_groups)
+            _lib.call("gprb_kff", _lib.DOT, f1.handle, f2.handle, float(sigma), float(sigma0), float(zeta), 0, 0.0,
+                      _lib.FF_FULL, 0, f1.n_groups, ptr(K), 3 * f2.n_groups, c_vp(0), 0, stream())
+            blocks.append(K)
+        return _host(blocks[0]), _host(interleave_stress(blocks[1], blocks[2], packs[0].n_groups))
     f1, f2 = force_pack(X1), force_pack(X2)
     K = empty(3 * f1.n_groups, 3 * f2.n_groups)
     _lib.call("gprb_kff", _lib.DOT, f1.handle, f2.handle, float(sigma), float(sigma0), float(zeta), 0, 0.0,

@@ -6,7 +6,7 @@ read like calls into the reference's cffi wrappers; the work is done by libgpr_b
 import torch
 
 from .. import _lib
-from ..device import Pack, energy_pack, force_pack, empty, ptr, stream, require_cuda, c_vp
+from ..device import Pack, energy_pack, force_pack, stress_packs, interleave_stress, empty, ptr, stream, require_cuda, c_vp
 
 
 def _host(t):
@@ -31,7 +31,19 @@ def kef_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False, stress=False, transpos
     """Energy-force block [m1, 3 m2] (or its transpose) (rbf_kernel.py:87-189)."""
     require_cuda()
     if stress:
-        raise NotImplementedError("stress blocks are not part of the B200 hot path yet (SURVEY.md §8f)")
+        # 9-column force data: C [m1, 3 m2] and C_s [m1, 6 m2] (rbf_kef_many_stress, rbf_kernel.cpp:256-338)
+        e = energy_pack(X1)
+        packs = stress_packs(X2)
+        blocks = []
+        for f in packs:
+            K = empty(e.n_groups, 3 * f.n_groups)
+            _lib.call("gprb_kef", _lib.RBF, e.handle, f.handle, float(sigma), float(l), float(zeta), 0, f.n_groups,
+                      ptr(K), 3 * f.n_groups, c_vp(0), 0, c_vp(0), 0, c_vp(0), 0, stream())
+            blocks.append(K)
+        m2 = packs[0].n_groups
+        Cs = interleave_stress(blocks[1].T.contiguous(), blocks[2].T.contiguous(), m2).T
+        C, Cs = _host(blocks[0]), _host(Cs.contiguous())
+        return (C.T, Cs.T) if transpose else (C, Cs)
     e, f = energy_pack(X1), force_pack(X2)
     K = empty(e.n_groups, 3 * f.n_groups)
     dK = empty(e.n_groups, 3 * f.n_groups) if grad else None
@@ -51,7 +63,17 @@ def kff_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False, stress=False, diag=Fal
     reference's `dK_dD > tol` pair cut; the grad variant does not (rbf_kernel.cpp:395 vs :534)."""
     require_cuda()
     if stress:
-        raise NotImplementedError("stress blocks are not part of the B200 hot path yet (SURVEY.md §8f)")
+        # X1 carries 9 columns: C [3 m1, 3 m2] and C_s [6 m1, 3 m2] (rbf_kff_many_stress, rbf_kernel.cpp:642-822);
+        # the pair cut `dK_dD > tol` applies as in the plain variant
+        packs = stress_packs(X1)
+        f2 = force_pack(X2)
+        blocks = []
+        for f1 in packs:
+            K = empty(3 * f1.n_groups, 3 * f2.n_groups)
+            _lib.call("gprb_kff", _lib.RBF, f1.handle, f2.handle, float(sigma), float(l), float(zeta), 1, float(tol),
+                      _lib.FF_FULL, 0, f1.n_groups, ptr(K), 3 * f2.n_groups, c_vp(0), 0, stream())
+            blocks.append(K)
+        return _host(blocks[0]), _host(interleave_stress(blocks[1], blocks[2], packs[0].n_groups))
     f1, f2 = force_pack(X1), force_pack(X2)
     K = empty(3 * f1.n_groups, 3 * f2.n_groups)
     dK = empty(3 * f1.n_groups, 3 * f2.n_groups) if grad else None

@@ -155,7 +155,9 @@ int gprb_predict(int m, int N, const double *Ks_dev, long long ldks, const doubl
  *   rad[w] = { I[nmax][lmax+1], dI/dr[nmax][lmax+1] }; rho[nq], G[nmax,nq] are the quadrature
  *   nodes and the combined weights g_n(rho) rho^2 e^{-a rho^2} sqrt(1-t^2) w (SO3.py:633,646-647).
  * gprb_so3_power     : c_nlm, power spectrum x[n_atoms,d], dxdr[n_seq,d,3] and seq[n_seq,2] (int64,
- *   atom indices local to the structure) (SO3.py:243-273, 655-727); seq_ptr = exclusive scan of nuniq. */
+ *   atom indices local to the structure) (SO3.py:243-273, 655-727); seq_ptr = exclusive scan of nuniq.
+ *   rdxdr != NULL (stress, SO3.py:253-273, 304-306): also rdxdr[n_seq,d,3,3] = -pstress / volume with
+ *   pos[n_atoms,3] the atom positions and inv_vol[S] = 1 / cell volume of each structure. */
 int gprb_so3_neighbors(int n_struct, int n_atoms, const int *atom_ptr, const int *struct_of,
                        const double *pos, const double *cell, const int *nimg, double rcut,
                        int mode, int *nnb, int *nuniq, const int *nb_ptr, int *nb_j, double *nb_rvec,
@@ -165,7 +167,8 @@ int gprb_so3_radial(int n_nb, const double *nb_rvec, int nmax, int lmax, int nq,
 int gprb_so3_power(int n_atoms, const int *nb_ptr, const int *nb_j, const double *nb_rvec, const double *rad,
                    const int *numbers, const int *atom_ptr, const int *struct_of, const int *seq_ptr,
                    int nmax, int lmax, double alpha, double rcut, const double *norm_l, int derivative,
-                   double *x, double *dxdr, long long *seq, void *stream);
+                   double *x, double *dxdr, long long *seq,
+                   const double *pos, const double *inv_vol, double *rdxdr, void *stream);
 
 #ifdef __cplusplus
 }

@@ -122,10 +122,12 @@ def expansion_coefficients(rvec, nmax, lmax, rcut, alpha):
     return C0 * fc[:, None, None, None], dC
 
 
-def so3_calculate(positions, cell, pbc, numbers, nmax=3, lmax=4, rcut=5.0, alpha=2.0):
+def so3_calculate(positions, cell, pbc, numbers, nmax=3, lmax=4, rcut=5.0, alpha=2.0, stress=False):
     """Power spectrum x [n, d], its derivative dxdr [n_seq, d, 3] and seq [n_seq, 2] (int64),
     with the reference's conventions (SO3.py:186-323): weights Z_j, norm_l, tril(n >= n') x l layout,
-    dxdr[(i, j)] = dx_i/dr_j summed over images, dxdr[(i, i)] = - sum_{j != i}."""
+    dxdr[(i, j)] = dx_i/dr_j summed over images, dxdr[(i, i)] = - sum_{j != i}.
+    stress=True also returns rdxdr [n_seq, d, 3, 3] = -pstress / volume (SO3.py:253-273, 304-306):
+    pstress[(i, j)] = -sum_w R_j(w) (x) dP(w), pstress[(i, i)] += R_i (x) sum_w dP(w)."""
     positions = np.asarray(positions, float)
     numbers = np.asarray(numbers)
     n = len(positions)
@@ -141,8 +143,10 @@ def so3_calculate(positions, cell, pbc, numbers, nmax=3, lmax=4, rcut=5.0, alpha
     row_of = {(int(a), int(b)): k for k, (a, b) in enumerate(seq)}
     x = np.zeros((n, d))
     dxdr = np.zeros((len(seq), d, 3))
+    pstress = np.zeros((len(seq), d, 3, 3))
+    vol = abs(np.linalg.det(cell))
     if not pairs:
-        return x, dxdr, seq
+        return (x, dxdr, seq, -pstress / vol) if stress else (x, dxdr, seq)
     pi = np.array([p[0] for p in pairs])
     pj = np.array([p[1] for p in pairs])
     S = np.array([p[2:] for p in pairs], dtype=float)
@@ -165,19 +169,25 @@ def so3_calculate(positions, cell, pbc, numbers, nmax=3, lmax=4, rcut=5.0, alpha
         dPt = dP[:, tril[0], tril[1]].reshape(len(sel), d, 3)
         for k, w in enumerate(sel):
             dxdr[row_of[(i, int(pj[w]))]] += dPt[k]
+            if stress:
+                pstress[row_of[(i, int(pj[w]))]] -= np.einsum('n,dm->dnm', positions[i] + rvec[w], dPt[k])
         ii = row_of[(i, i)]
         own = [row_of[(i, j)] for j in sorted(nb_sets[i])]
         dxdr[ii] -= dxdr[own].sum(axis=0)
+        if stress:
+            pstress[ii] += np.einsum('n,dm->dnm', positions[i], dPt.sum(axis=0))
+    if stress:
+        return x, dxdr, seq, -pstress / vol
     return x, dxdr, seq
 
 
 class SO3Oracle:
     """Descriptor-protocol wrapper (calculate(atoms) -> dict) around so3_calculate."""
 
-    def __init__(self, nmax=3, lmax=4, rcut=5.0, alpha=2.0):
-        self.nmax, self.lmax, self.rcut, self.alpha = nmax, lmax, rcut, alpha
+    def __init__(self, nmax=3, lmax=4, rcut=5.0, alpha=2.0, stress=False):
+        self.nmax, self.lmax, self.rcut, self.alpha, self.stress = nmax, lmax, rcut, alpha, stress
 
     def calculate(self, atoms, atom_ids=None, use_mpi=False):
-        x, dxdr, seq = so3_calculate(atoms.positions, np.asarray(atoms.cell), atoms.pbc, atoms.numbers,
-                                     self.nmax, self.lmax, self.rcut, self.alpha)
-        return {'x': x, 'dxdr': dxdr, 'rdxdr': None, 'elements': list(atoms.symbols), 'seq': seq}
+        r = so3_calculate(atoms.positions, np.asarray(atoms.cell), atoms.pbc, atoms.numbers,
+                          self.nmax, self.lmax, self.rcut, self.alpha, stress=self.stress)
+        return {'x': r[0], 'dxdr': r[1], 'rdxdr': r[3] if self.stress else None, 'elements': list(atoms.symbols), 'seq': r[2]}

@@ -84,8 +84,8 @@ def test_fit_and_predict_structure_vs_golden(g):
     assert np.all(np.isfinite(out[2])) and np.all(np.isfinite(out[5]))
     E2, F2, _ = gp.predict_structure(test, stress=False)
     assert E2 == E and np.array_equal(F2, F)
-    with pytest.raises(NotImplementedError):
-        gp.predict_structure(test)            # reference default stress=True: not on the hot path yet
+    with pytest.raises(ValueError):
+        gp.predict_structure(test)            # reference default stress=True needs SO3(stress=True) (tests/test_stress.py)
 
 
 def test_optimisation_trajectory_vs_golden(g):
