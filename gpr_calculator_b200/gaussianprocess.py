@@ -14,8 +14,9 @@ where the arithmetic runs:
   block of K / dK, K is all-gathered, the gradient trace is all-reduced (dist.py).  This replaces
   the mpi4py gather/bcast and the redundant allreduce of :246-247.
 
-Persistence to an ASE database (:632-821) needs ASE and is outside the hot path;
-the json part of save/load is kept.
+Persistence (:632-821): the json model file plus an ASE sqlite database of the labelled structures,
+read and written by gpr_calculator_b200.asedb (ASE's file layout, no ASE needed); GP.load recomputes
+the descriptors in batches on the device.
 """
 import json
 import logging
@@ -583,7 +584,7 @@ class GP():
             self.train_y['force'] = F
 
     # ---------------------------------------------------------------------------------------------
-    # persistence (json part only; the ASE-db part needs ASE — SURVEY.md §8f #2)
+    # persistence: json model file + ASE sqlite database
     # ---------------------------------------------------------------------------------------------
     def save_dict(self, db_filename):
         noise = {"energy": self.noise_e, "force": self.noise_f, "f_coef": self.f_coef, "bounds": self.noise_bounds}
@@ -603,23 +604,22 @@ class GP():
             print(f"save model to {filename} and {db_filename}")
 
     def export_ase_db(self, db_filename, permission="w"):
-        try:
-            from ase.db import connect
-        except ImportError as exc:
-            raise ImportError("GP.export_ase_db needs ASE (ase.db); it is outside the B200 hot path") from exc
-        if permission == "w" and os.path.exists(db_filename):
-            os.remove(db_filename)
-        with connect(db_filename, serial=True) as db:
-            for (struc, energy, force, energy_in, force_in, _, _) in self.train_db:
-                actual_energy, actual_forces = deepcopy(energy), force.copy()
-                if self.base_potential is not None:
-                    energy_off, force_off, _ = self.compute_base_potential(struc)
-                    actual_energy += energy_off
-                    actual_forces += force_off
-                data = {"energy": energy, "force": force, "energy_in": energy_in, "force_in": force_in}
-                kvp = {"dft_energy": actual_energy / len(force), "dft_fmax": np.max(np.abs(actual_forces.flatten()))}
-                struc.set_constraint()
-                db.write(struc, data=data, key_value_pairs=kvp)
+        """Write the training structures and their labels to an ASE sqlite database
+        (gaussianprocess.py:689-724).  The rows are written by gpr_calculator_b200.asedb (ASE's own
+        file layout), so ASE is not needed and the file can be opened with ase.db.connect."""
+        from . import asedb
+        rows = []
+        for (struc, energy, force, energy_in, force_in, _, _) in self.train_db:
+            actual_energy, actual_forces = deepcopy(energy), np.array(force, dtype=float)
+            if self.base_potential is not None:
+                energy_off, force_off, _ = self.compute_base_potential(struc)
+                actual_energy += energy_off
+                actual_forces += force_off
+            data = {"energy": float(energy), "force": np.asarray(force, dtype=np.float64), "energy_in": bool(energy_in),
+                    "force_in": [int(i) for i in force_in]}
+            kvp = {"dft_energy": float(actual_energy) / len(force), "dft_fmax": float(np.max(np.abs(actual_forces.flatten())))}
+            rows.append((struc, kvp, data))
+        asedb.write_rows(db_filename, rows, append=(permission != "w"))
 
     @classmethod
     def load(cls, filename, N_max=None, device='cuda'):
@@ -632,21 +632,27 @@ class GP():
             print(instance)
         return instance
 
-    def extract_db(self, db_filename, N_max=None):
-        """Recompute descriptors for the structures of an ASE database (:726-821)."""
-        try:
-            from ase.db import connect
-        except ImportError as exc:
-            raise ImportError("GP.extract_db needs ASE (ase.db); it is outside the B200 hot path") from exc
+    def extract_db(self, db_filename, N_max=None, batch=16):
+        """Rebuild the training set from an ASE database (gaussianprocess.py:726-821): the descriptors
+        of all structures are recomputed, `batch` structures per device pass (the reference recomputes
+        them one by one, split over MPI ranks)."""
+        from . import asedb
+        rows = []
+        for n, row in enumerate(asedb.read_rows(db_filename)):
+            if N_max is not None and n >= N_max:
+                break
+            rows.append(row)
         pts = {"energy": [], "force": [], "db": []}
-        with connect(db_filename, serial=True) as db:
-            for n, row in enumerate(db.select()):
-                if N_max is not None and n >= N_max:
-                    break
-                atoms = db.get_atoms(id=row.id)
-                energy, force = row.data.energy, row.data.force.copy()
-                energy_in, force_in = row.data.energy_in, row.data.force_in
-                d = self.descriptor.calculate(atoms)
+        for s0 in range(0, len(rows), batch):
+            part = rows[s0:s0 + batch]
+            atoms_list = [r.toatoms() for r in part]
+            if hasattr(self.descriptor, "calculate_batch"):
+                descs = self.descriptor.calculate_batch(atoms_list, to_host=True)
+            else:
+                descs = [self.descriptor.calculate(a) for a in atoms_list]
+            for row, atoms, d in zip(part, atoms_list, descs):
+                energy, force = float(row.data["energy"]), np.array(row.data["force"], dtype=float)
+                energy_in, force_in = bool(row.data["energy_in"]), [int(i) for i in row.data["force_in"]]
                 ele = atomic_numbers(d['elements'])
                 if energy_in:
                     pts["energy"].append((d['x'], energy / len(atoms), ele))
