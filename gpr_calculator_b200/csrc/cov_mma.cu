@@ -178,11 +178,13 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
     int ga, gb;
     {
         const int G = P.n_groupsB;
-        ga = (int)((long long)G * blockIdx.y / P.n_splits);
-        gb = (int)((long long)G * (blockIdx.y + 1) / P.n_splits);
         const int first_group = P.sched_ent[ent0].x, last_group = P.sched_ent[ent0 + nent - 1].x;
-        if (P.mode == GPRB_FF_SYMMETRIC || P.mode == GPRB_FF_UPPER) ga = max(ga, first_group);
-        if (P.mode == GPRB_FF_DIAG) { ga = max(ga, first_group); gb = min(gb, last_group + 1); }
+        // the column groups this row block sweeps, cut evenly over the n_splits CTAs of the block
+        int lo = 0, hi = G;
+        if (P.mode == GPRB_FF_SYMMETRIC || P.mode == GPRB_FF_UPPER) lo = first_group;
+        if (P.mode == GPRB_FF_DIAG) { lo = first_group; hi = last_group + 1; }
+        ga = lo + (int)((long long)(hi - lo) * blockIdx.y / P.n_splits);
+        gb = lo + (int)((long long)(hi - lo) * (blockIdx.y + 1) / P.n_splits);
     }
     if (gb <= ga) return;
     const int cr0 = P.row_ptrB[ga], cr1 = P.row_ptrB[gb];
@@ -546,7 +548,9 @@ int fill_kernel_params(CovParams &P, int kernel, double p0, double p1, double ze
 int choose_splits(int n_blocks, int n_groupsB) {
     int sms = 148;
     int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int want = (4 * sms + n_blocks - 1) / (n_blocks > 0 ? n_blocks : 1);
+    // enough CTAs (24 per SM) that the longest one is a small fraction of the launch: a row block's sweep
+    // can take tens of milliseconds, and whole-sweep CTAs would leave a long partially filled last wave
+    int want = (24 * sms + n_blocks - 1) / (n_blocks > 0 ? n_blocks : 1);
     if (want < 1) want = 1;
     if (want > n_groupsB) want = n_groupsB;
     if (want < 1) want = 1;

@@ -100,10 +100,15 @@ __global__ void __launch_bounds__(256) trace_kernel(int N, int r0, int r1, const
         if (dK) {
             const double *di = dK + (long long)(i - r0) * lddk;
             if (upper_only) {
-                for (int j = i + threadIdx.x; j < N; j += blockDim.x) {
+                // upper_only == 2 (row-sharded build): energy rows hold K_ee only, force rows hold K_fe and the
+                // J >= I blocks of K_ff:  tr = EE (upper, doubled) + 2 FE + FF (upper, doubled)
+                const int jend = (upper_only == 2 && i < NE) ? NE : N;
+                for (int j = i + threadIdx.x; j < jend; j += blockDim.x) {
                     const double t = fma(ai, alpha[j], -ki[j]) * di[j];
                     acc += (j == i) ? t : 2.0 * t;
                 }
+                if (upper_only == 2 && i >= NE)
+                    for (int j = threadIdx.x; j < NE; j += blockDim.x) acc += 2.0 * fma(ai, alpha[j], -ki[j]) * di[j];
             } else {
                 for (int j = threadIdx.x; j < N; j += blockDim.x) acc = fma(fma(ai, alpha[j], -ki[j]), di[j], acc);
             }
@@ -338,6 +343,26 @@ extern "C" int gprb_predict(int m, int N, const double *Ks, long long ldks, cons
         if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDgemm status %d", (int)bs); return GPRB_ERR_CUDA; }
     }
     predict_rows_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, var ? work : nullptr, diag, mean, var);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+// dst[j][i] = src[i][j] for a rows x cols block (32 x 32 tiles through shared memory)
+__global__ void transpose_copy_kernel(double *dst, long long ldd, const double *src, long long lds, int rows, int cols) {
+    __shared__ double t[32][33];
+    const int i = blockIdx.y * 32 + threadIdx.y, j = blockIdx.x * 32 + threadIdx.x;
+    if (i < rows && j < cols) t[threadIdx.y][threadIdx.x] = src[(long long)i * lds + j];
+    __syncthreads();
+    const int tj = blockIdx.x * 32 + threadIdx.y, ti = blockIdx.y * 32 + threadIdx.x;   // dst row = src col
+    if (tj < cols && ti < rows) dst[(long long)tj * ldd + ti] = t[threadIdx.x][threadIdx.y];
+}
+
+extern "C" int gprb_transpose_copy(double *dst, long long ldd, const double *src, long long lds, int rows, int cols, void *stream) {
+    GPRB_REQUIRE(dst && src && rows >= 0 && cols >= 0, "gprb_transpose_copy: bad argument");
+    if (rows == 0 || cols == 0) return GPRB_OK;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 32);
+    transpose_copy_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(dst, ldd, src, lds, rows, cols);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;

@@ -234,7 +234,7 @@ def _at(t, r, c):
     return c_vp(0) if t is None else c_vp(t.data_ptr() + (r * t.stride(0) + c) * t.element_size())
 
 
-def build_energy_rows(kernel, p0, p1, zeta, side1, side2, window, K, dK=None, zeta_ef=None, kfe_rows=None):
+def build_energy_rows(kernel, p0, p1, zeta, side1, side2, window, K, dK=None, zeta_ef=None, kfe_rows=None, skip_kef=False):
     """Rows of side-1 energy groups [ea, eb): K[:, :NE2] = K_ee, K[:, NE2:] = K_ef.
 
     K / dK: [eb - ea, NE2 + 3 NF2] row-major views (a row stride > n_cols is fine).  When `kfe_rows`
@@ -252,7 +252,7 @@ def build_energy_rows(kernel, p0, p1, zeta, side1, side2, window, K, dK=None, ze
     ldd = dK.stride(0) if dK is not None else 0
     if e2 is not None:
         _lib.call("gprb_kee", kernel, e1.handle, e2.handle, p0, p1, float(zeta), ea, eb, _at(K, 0, 0), ld, _at(dK, 0, 0), ldd, st)
-    if f2 is None:
+    if f2 is None or skip_kef:
         return
     Kfe, dKfe = kfe_rows if kfe_rows is not None else (None, None)
     if (ea, eb) == (0, e1.n_groups):

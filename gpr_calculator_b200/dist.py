@@ -18,8 +18,9 @@ def world():
     return 0, 1
 
 
-def split_groups(costs, parts):
-    """Contiguous partition of len(costs) groups into `parts` blocks with balanced total cost.
+def split_groups(costs, parts, speed=None):
+    """Contiguous partition of len(costs) groups into `parts` blocks with balanced total cost
+    (block p gets a share proportional to speed[p] when given).
 
     Returns `parts + 1` boundaries b with b[0] = 0 and b[-1] = len(costs)."""
     costs = np.asarray(costs, dtype=np.float64)
@@ -28,9 +29,11 @@ def split_groups(costs, parts):
         return [0] * (parts + 1)
     cum = np.concatenate(([0.0], np.cumsum(costs)))
     total = cum[-1]
+    share = np.ones(parts) if speed is None else np.asarray(speed, dtype=np.float64)
+    share = np.cumsum(share) / share.sum()
     bounds = [0]
     for p in range(1, parts):
-        target = total * p / parts
+        target = total * share[p - 1]
         j = int(np.searchsorted(cum, target, side="left"))
         if j > 0 and abs(cum[j - 1] - target) <= abs(cum[min(j, n)] - target):
             j -= 1
@@ -40,18 +43,19 @@ def split_groups(costs, parts):
     return bounds
 
 
-def row_windows(e_rows, f_rows, parts, upper=False):
+def row_windows(e_rows, f_rows, parts, upper=False, speed=None):
     """Per-rank windows ((e0,e1),(f0,f1)) over energy groups and force groups.
 
     Energy and force groups are partitioned independently so that every rank gets an equal share
     of both block rows (the force block dominates: cost ~ rows of the centre).  upper=True balances
     the trapezoids of an upper-triangle build (GPRB_FF_UPPER): force group I costs
-    n_I * sum_{J >= I} n_J."""
+    n_I * sum_{J >= I} n_J.  speed[r] (relative measured throughput of rank r, see GP._build_K) scales
+    the share of the force rows rank r receives."""
     eb = split_groups(e_rows, parts)
     f = np.asarray(f_rows, dtype=np.float64)
     if upper and len(f):
         f = f * np.cumsum(f[::-1])[::-1]
-    fb = split_groups(f, parts)
+    fb = split_groups(f, parts, speed=speed)
     return [((eb[r], eb[r + 1]), (fb[r], fb[r + 1])) for r in range(parts)]
 
 
@@ -99,6 +103,17 @@ def gather_rows_inplace(K, windows, NE, group=None):
             if s.numel():
                 dist.broadcast(s, src=r if group is None else dist.get_global_rank(group, r), group=group)
     return K
+
+
+def all_gather_floats(value, device="cpu", group=None):
+    """One python float per rank -> list of all ranks' values."""
+    rank, size = world()
+    if size == 1:
+        return [float(value)]
+    t = torch.zeros(size, dtype=torch.float64, device=device)
+    t[rank] = float(value)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return [float(v) for v in t.cpu()]
 
 
 def all_reduce_sum(values, device="cpu", group=None):

@@ -186,19 +186,43 @@ class GP():
         from .device import build_energy_rows, build_force_rows
         args = self.kernel.cov_args(grad=grad, f_tol=f_tol)
         has_dk = args.pop("has_dk") and grad
-        windows = gdist.row_windows(e.indices if e is not None else [], f.indices if f is not None else [], size, upper=True)
+        # force windows follow the measured throughput of the ranks (updated after every build)
+        speed = getattr(self, "_shard_speed", None)
+        if speed is None or len(speed) != size:
+            speed = np.ones(size)
+        f_rows = f.indices if f is not None else []
+        windows = gdist.row_windows(e.indices if e is not None else [], f_rows, size, upper=True, speed=speed)
         (e0, e1), (f0, f1) = windows[rank]
         n_loc = (e1 - e0) + 3 * (f1 - f0)
         K = torch.empty((N, N), dtype=F64, device="cuda")
         dK = torch.zeros((n_loc, N), dtype=F64, device="cuda") if has_dk else None
         ff = dict(use_tol=args.pop("use_tol"), tol=args.pop("tol"), zeta_ff=args.pop("zeta_ff"))
+        # energy rows: K_ee only; K_ef is the transpose of the K_fe rows the force windows produce
         build_energy_rows(side1=(e, f), side2=(e, f), window=(e0, e1), K=K[e0:e1],
-                          dK=None if dK is None else dK[:e1 - e0], **args)
+                          dK=None if dK is None else dK[:e1 - e0], skip_kef=True, **args)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
         build_force_rows(side1=(e, f), side2=(e, f), window=(f0, f1), K=K[NE + 3 * f0:NE + 3 * f1],
                          dK=None if dK is None else dK[e1 - e0:], ff_mode=_lib.FF_UPPER, **args, **ff)
+        t1.record()
         gdist.gather_rows_inplace(K, windows, NE)
+        st = stream()
         if NF:
-            _lib.call("gprb_symmetrize", c_vp(K.data_ptr() + (NE * N + NE) * 8), N, 3 * NF, stream())
+            _lib.call("gprb_symmetrize", c_vp(K.data_ptr() + (NE * N + NE) * 8), N, 3 * NF, st)
+            if NE:
+                _lib.call("gprb_transpose_copy", c_vp(K.data_ptr() + NE * 8), N, c_vp(K.data_ptr() + NE * N * 8), N,
+                          3 * NF, NE, st)
+            # re-balance: share of rank r ~ (cost it handled) / (time it took), damped
+            t1.synchronize()
+            rows = np.asarray(f_rows, dtype=np.float64)
+            cost = rows * np.cumsum(rows[::-1])[::-1]
+            mine = float(cost[f0:f1].sum()) / max(t0.elapsed_time(t1), 1e-3)
+            rates = np.asarray(gdist.all_gather_floats(mine, device="cuda"))
+            if np.all(rates > 0):
+                self._shard_speed = 0.5 * speed / speed.sum() + 0.5 * rates / rates.sum()
+            if os.environ.get("GPRB_DEBUG_SHARD"):
+                print("[shard] rank %d window %d:%d kff %.1f ms speed %s" % (rank, f0, f1, t0.elapsed_time(t1),
+                                                                          np.round(self._shard_speed, 4)), flush=True)
         return K, dK, [(e0, e1), (NE + 3 * f0, NE + 3 * f1)]
 
     def _factor(self, K, noise_e, noise_f):
@@ -271,7 +295,7 @@ class GP():
                 if is_rbf:
                     dptr = c_vp(dK.data_ptr() + off * dK.stride(0) * 8)
                 _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, dptr, N, NE,
-                          float(noise_e) ** 2, float(noise_f) ** 2, 1, out, st)
+                          float(noise_e) ** 2, float(noise_f) ** 2, 2 if sharded else 1, out, st)
                 g_l += out[0]
                 half_w_noise += out[1]
                 _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, c_vp(0), N, NE,

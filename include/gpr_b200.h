@@ -118,6 +118,8 @@ int gprb_chol_inverse(const double *L_dev, long long ldl, int N, double *Kinv_de
 /* A[i][j] = A[j][i] for all i > j of the n x n block at A (fills the lower triangle from the upper
  * one after an all-gather of GPRB_FF_UPPER row blocks). */
 int gprb_symmetrize(double *A_dev, long long ld, int n, void *stream);
+/* dst[j*ldd + i] = src[i*lds + j] for a rows x cols block (K_ef = K_fe^T after a row-sharded build). */
+int gprb_transpose_copy(double *dst_dev, long long ldd, const double *src_dev, long long lds, int rows, int cols, void *stream);
 /* out_host[0] = sum_i log L_ii ; out_host[1] = y.alpha                 (gaussianprocess.py:183-186) */
 int gprb_lml_terms(const double *L_dev, long long ldl, int N, const double *y_dev, const double *alpha_dev,
                    double *out_host, void *stream);
@@ -125,8 +127,10 @@ int gprb_lml_terms(const double *L_dev, long long ldl, int N, const double *y_de
  * rows [r0,r1) only (row-block sharded; all-reduce the scalar across ranks).
  * out_host[1] = 1/2 sum_i (alpha_i^2 - Kinv_ii) * w_i, w_i = (i<NE ? we : wf) over the same rows
  * (noise / sigma terms).                                           (gaussianprocess.py:188-198)
- * upper_only != 0: dK holds valid entries only for columns j >= i (GPRB_FF_UPPER build); the sum
- * then runs over j >= i with weight 2 off the diagonal (W and dK are symmetric). */
+ * upper_only = 1: dK holds valid entries only for columns j >= i (GPRB_FF_UPPER build); the sum
+ * then runs over j >= i with weight 2 off the diagonal (W and dK are symmetric).
+ * upper_only = 2: row-sharded build: energy rows (i < NE) hold dK_ee only, force rows hold dK_fe and
+ * the J >= I blocks of dK_ff: sum = EE (j in [i, NE), doubled) + 2 FE + FF (j >= i, doubled). */
 int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha_dev, const double *Kinv_dev, long long ldi,
                         const double *dK_rows_dev, long long lddk, int NE, double we, double wf,
                         int upper_only, double *out_host, void *stream);

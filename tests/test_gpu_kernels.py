@@ -214,6 +214,45 @@ def test_upper_mode_windows_symmetrize_and_trace():
         assert abs(out_full[1] - out_up[1]) <= 1e-12 * abs(out_full[1])
 
 
+def test_trace_sharded_mode_and_transpose():
+    """gprb_lml_grad_trace(upper_only=2) reads K_ee (upper), K_fe and K_ff (upper) only and must equal the full
+    trace; gprb_transpose_copy fills K_ef from K_fe."""
+    import ctypes
+    from gpr_calculator_b200 import _lib
+    from gpr_calculator_b200.device import Pack, k_total_device, ptr, stream, c_vp
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(21)
+    X, dX, ELE, ind = list_to_tuple(make_force(rng, 17, lo=5, hi=30))
+    Xe, Ee, inde = list_to_tuple(make_energy(rng, 6, lo=5, hi=30), mode="energy")
+    f, e = Pack(X, ELE, ind, dxdr=dX), Pack(Xe, Ee, inde)
+    K, dK = k_total_device(_lib.RBF, 1.2, 0.7, 2.0, (e, f), None, use_tol=False, grad=True)
+    NE, N = 6, 6 + 51
+    alpha = torch.randn(N, dtype=torch.float64, device="cuda")
+    W = torch.randn(N, N, dtype=torch.float64, device="cuda")
+    W = W + W.T
+    want = 0.5 * ((torch.outer(alpha, alpha) - W) * dK).sum().item()
+    poisoned = dK.clone()
+    poisoned[:NE, NE:] = float("nan")                                    # K_ef: never read in mode 2
+    poisoned[NE:, NE:] = torch.where(torch.triu(torch.ones(N - NE, N - NE, dtype=torch.bool, device="cuda")), dK[NE:, NE:],
+                                     torch.full_like(dK[NE:, NE:], float("nan")))
+    poisoned[:NE, :NE] = torch.where(torch.triu(torch.ones(NE, NE, dtype=torch.bool, device="cuda")), dK[:NE, :NE],
+                                     torch.full_like(dK[:NE, :NE], float("nan")))
+    out = (ctypes.c_double * 2)()
+    _lib.call("gprb_lml_grad_trace", N, 0, N, ptr(alpha), ptr(W), N, ptr(poisoned), N, NE, 0.1, 0.2, 2, out, stream())
+    assert abs(out[0] - want) <= 1e-10 * abs(want)
+    # two row ranges, as a rank holds them
+    tot = 0.0
+    for r0, r1 in ((0, 2), (2, NE), (NE, NE + 21), (NE + 21, N)):
+        _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(W), N, c_vp(poisoned.data_ptr() + r0 * N * 8), N, NE,
+                  0.1, 0.2, 2, out, stream())
+        tot += out[0]
+    assert abs(tot - want) <= 1e-10 * abs(want)
+    Kt = K.clone()
+    Kt[:NE, NE:] = float("nan")
+    _lib.call("gprb_transpose_copy", c_vp(Kt.data_ptr() + NE * 8), N, c_vp(Kt.data_ptr() + NE * N * 8), N, N - NE, NE, stream())
+    assert torch.equal(Kt, K) or (Kt - K).abs().max().item() <= 1e-15 * K.abs().max().item()
+
+
 def test_flat_tiles_share_groups():
     """Groups that start and end in the middle of 8-row tiles and of 64-row CTA blocks on both sides,
     empty groups, and a row window that starts inside a tile."""
