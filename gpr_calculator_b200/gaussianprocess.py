@@ -892,17 +892,21 @@ class GP():
         return pts_to_add, N_pts, errors
 
     def sparsify(self, e_tol=1e-10, f_tol=1e-10):
-        """Drop training points in the near-null space of K (CUR, :1004-1023)."""
-        K = self.kernel.k_total(self.train_x)
+        """Drop training points in the near-null space of K (CUR, gaussianprocess.py:1004-1023).  K stays on
+        the device: eigen-decomposition by cuSOLVER syevd (torch.linalg.eigh), leverage scores there; the
+        O(N_f^2) Python double loop of the reference is a vectorised membership test."""
+        require_cuda()
+        K, _ = self.kernel.k_total_device(self.train_x, None, grad=False)
         N_e = len(self.train_x["energy"][-1])
         N_f = len(self.train_x["force"][-1])
-        pts_e = CUR(K[:N_e, :N_e], e_tol)
-        pts = CUR(K[N_e:, N_e:], f_tol)
+        pts_e = CUR_device(K[:N_e, :N_e], e_tol)
+        pts = CUR_device(K[N_e:, N_e:], f_tol)
         pts_f = []
         if N_f > 1:
-            for i in range(N_f):
-                if all(np.sum(pts == i * 3 + c) == 1 for c in range(3)):
-                    pts_f.append(i)
+            hit = np.zeros(3 * N_f, dtype=bool)
+            hit[pts] = True
+            pts_f = [int(i) for i in np.flatnonzero(hit.reshape(N_f, 3).all(axis=1))]
+        pts_e = [int(i) for i in pts_e]
         print("{:d} energy and {:d} forces will be removed".format(len(pts_e), len(pts_f)))
         if len(pts_e) + len(pts_f) > 0:
             self.remove_train_pts(pts_e, pts_f)
@@ -984,6 +988,19 @@ class GP():
 import ctypes  # noqa: E402
 
 ctypes_double = ctypes.c_double
+
+
+def CUR_device(K, l_tol=1e-10):
+    """CUR on a device-resident block: same selection as CUR() below."""
+    if K.shape[0] == 0:
+        return np.zeros(0, dtype=np.int64)
+    L, U = torch.linalg.eigh(K)
+    low = L < l_tol
+    n_low = int(low.sum())
+    if n_low == 0:
+        return np.zeros(0, dtype=np.int64)
+    omega = (U[:, low] ** 2).sum(dim=1)
+    return torch.argsort(-omega, stable=True)[:n_low].cpu().numpy()
 
 
 def CUR(K, l_tol=1e-10):

@@ -209,3 +209,27 @@ def test_inverse_large_n_route_matches_potri(monkeypatch):
     ref = np.linalg.inv(K)
     for o in outs:
         assert rel_err(o, ref) <= 1e-10 and np.abs(o - o.T).max() == 0.0
+
+
+def test_sparsify_removes_duplicated_points(g):
+    """CUR sparsification on device (gaussianprocess.py:1004-1023, 1165-1182): an exactly duplicated training
+    structure puts K's smallest eigenvalues below the tolerance and its rows are dropped."""
+    from gpr_calculator_b200.gaussianprocess import GP, CUR, CUR_device
+    from gpr_calculator_b200.kernels import RBF_mb
+    from gpr_calculator_b200.SO3 import SO3
+    from gpr_calculator_b200.utilities import convert_train_data
+    import torch
+    des = SO3(nmax=3, lmax=4, rcut=5.0)
+    lab = [(_atoms(g, g["t%d_pos" % k], fixed=False), float(g["t%d_E" % k]), g["t%d_F" % k]) for k in (0, 1, 0)]   # third = first
+    gp = GP(kernel=RBF_mb(para=[2.0, 0.8], zeta=2.0), descriptor=des, noise_e=0.002, noise_f=0.1, log_file=None)
+    with contextlib.redirect_stdout(io.StringIO()):
+        gp.fit(TrainData=convert_train_data(lab, des), opt=False, show=False)
+        n_e, n_f = gp.N_energy, gp.N_forces
+        K = gp.kernel.k_total(gp.train_x)
+        # device and host selections agree
+        sel_h = CUR(K[:n_e, :n_e], 1e-8)
+        sel_d = CUR_device(torch.as_tensor(K[:n_e, :n_e], device="cuda"), 1e-8)
+        assert sorted(sel_h.tolist()) == sorted(sel_d.tolist()) and len(sel_d) == 1
+        gp.sparsify(e_tol=1e-8, f_tol=1e-8)
+    assert len(gp.train_x["energy"][-1]) == n_e - 1 and len(gp.train_x["force"][-1]) == n_f - 13
+    assert len(gp.y_train) == (n_e - 1) + 3 * (n_f - 13) and gp.alpha_ is not None
