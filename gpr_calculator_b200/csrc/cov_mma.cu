@@ -24,8 +24,10 @@
 //  * column tiles stream through a ring of TMA stages (cp.async.bulk + mbarrier); the warp that
 //    releases a stage last refills it — no producer warp and no CTA-wide barrier in the main loop.
 //  * flush at the end of a column group: transposing butterfly over the 4 lanes of a row, segmented
-//    suffix sum over the 8 rows of the warp, head rows to shared memory; the LAST warp to arrive
-//    adds the per-warp partials in a fixed order and writes the 3x3 block (deterministic).
+//    suffix sum over the 8 rows of the warp, head rows to one of four shared-memory buffers, one
+//    mbarrier arrival per warp.  Two flushes later every warp adds the per-warp partials of its share
+//    of the outputs in a fixed order and writes them (deterministic; no atomics on the critical path,
+//    no designated finisher).
 //    Row groups that continue in a neighbouring CTA are combined with fp64 atomics into the
 //    pre-zeroed output (two addends: still order independent).
 #include "common.cuh"
@@ -40,6 +42,7 @@ constexpr int STAGES = 2;
 constexpr int CH = GPRB_CHUNK_TILES;
 constexpr int REC = GPRB_REC_INTS;
 constexpr int MAXROWS = WARPS * 8;
+constexpr int NFB = 4;                 // flush buffers: partials of flush k are summed two flushes later
 
 struct CovParams {
     const double *PA; const int *eleA; const int *row_groupA;
@@ -85,6 +88,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try(bar, parity))
         if (clock64() - t0 > SPIN_LIMIT_CYCLES) spin_timeout(1);
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -95,20 +101,23 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 }
 
 // exp(x) for x <= 0 (the RBF exponent -(1-D)/(2 l^2)): 2^(k/32) table + degree-5 polynomial on
-// |r| <= ln2/64 (truncation 2e-15 relative).  10 FP64 instructions instead of the ~25 of exp().
+// |r| <= ln2/64 (truncation 2e-15 relative), evaluated in Estrin form to keep the dependent chain short
+// (every FP64 instruction of the epilogue queues behind other warps' DMMAs).
 __device__ __forceinline__ double exp_neg(double x, const double *tab) {
-    if (x < -700.0) return 0.0;
+    x = fmax(x, -700.0);                                     // exp(-700) ~ 1e-304: below anything that matters, no branch
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: low word = round-to-nearest integer
     const double t = fma(x, 46.16624130844682903, MAGIC);    // 32 / ln 2
     const int ki = __double2loint(t);
     const double kf = t - MAGIC;
     double r = fma(kf, -0x1.62e42fe000000p-6, x);            // ln2/32, high 29 bits (kf * hi is exact)
     r = fma(kf, -0x1.f473de6af278fp-35, r);                   // ln2/32 - high part
-    double p = fma(r, 8.33333333333333322e-03, 4.16666666666666644e-02);
-    p = fma(p, r, 1.66666666666666657e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    const double r2 = r * r;
+    const double a = fma(r, 1.66666666666666657e-01, 0.5);
+    const double b = fma(r, 8.33333333333333322e-03, 4.16666666666666644e-02);
+    const double c1 = 1.0 + r;
+    const double d = fma(r2, a, c1);
+    const double r4 = r2 * r2;
+    const double p = fma(r4, b, d);                           // 1 + r + r^2/2 + r^3/6 + r^4/24 + r^5/120
     const double v = tab[ki & 31] * p;
     return __hiloint2double(__double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
 }
@@ -133,17 +142,21 @@ __device__ __forceinline__ void pair_weights(const CovParams &P, const double *t
     const double sm2 = pow_zm2<ZI>(s, P.zeta, P.zi);
     const double sm1 = s * sm2;
     if (KERNEL == GPRB_KERNEL_RBF) {
+        // every weight is E times a factor that does not depend on E: the factors are computed next to the exp
+        // chain (instruction-level parallelism), one multiply each once E is known
         const double D = s * sm1;
+        const double f1 = P.kz * sm1;                                  // w1 = g beta          = E f1
+        const double q2 = f1 * (P.zeta * sm1);                         // g zeta^2 s^(2zeta-2) = E q2
+        const double f2 = (ZI == 2) ? fma(q2, P.c, P.kz) : fma(q2, P.c, P.kz * (P.zeta - 1.0) * sm2);   // w2 = g gamma = E f2
+        const double h = fma(-P.c_il3, D, P.h0);                       // (1-D)/l^3 - 2/l   (:622-630, :245-247)
+        const double g1 = f1 * h, g2 = fma(f2, h, -(q2 * P.c_il3));
         const double E = exp_neg(fma(D, P.c, -P.c), tab);             // exp(-(1-D)/(2l^2))  rbf_kernel.cpp:393
         if (FF && !GRAD && P.use_tol) valid = valid && (E * P.k1 > P.tol);   // dK_dD > tol (:394-395), non-grad only
-        const double gz = E * P.kz;                                    // g * zeta
-        w1 = gz * sm1;                                                 // g * beta
-        const double z2 = w1 * (P.zeta * sm1);                         // g zeta^2 s^(2zeta-2)
-        if (FF) w2 = (ZI == 2) ? fma(z2, P.c, gz) : fma(z2, P.c, gz * (P.zeta - 1.0) * sm2);   // g * gamma
+        w1 = E * f1;
+        if (FF) w2 = E * f2;
         if (GRAD) {
-            const double h = fma(-P.c_il3, D, P.h0);                   // (1-D)/l^3 - 2/l   (:622-630, :245-247)
-            u1 = w1 * h;
-            if (FF) u2 = fma(w2, h, -(z2 * P.c_il3));
+            u1 = E * g1;
+            if (FF) u2 = E * g2;
         }
     } else {   // Dot: sigma^2 zeta (s^(z-1) G + (z-1) s^(z-2) p q^T)   (dot_kernel.cpp:285-289, dot_kernel.py:256)
         w1 = P.c_dot * sm1;
@@ -163,12 +176,13 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sA = reinterpret_cast<double *>(smem_raw);                  // [WARPS][a_tile_d]
     double *sB = sA + WARPS * a_tile_d;                                  // [STAGES][CH][b_tile_d]
-    double *sRow = sB + STAGES * CH * b_tile_d;                          // [2][MAXROWS][NT]
-    double *sTab = sRow + 2 * MAXROWS * NT;                              // [32]
+    double *sRow = sB + STAGES * CH * b_tile_d;                          // [NFB][MAXROWS][NT] flush partials
+    double *sTab = sRow + NFB * MAXROWS * NT;                            // [32]
     int4 *sEnt = reinterpret_cast<int4 *>(sTab + 32);                    // [MAXROWS]
     int *sRec = reinterpret_cast<int *>(sEnt + MAXROWS);                 // [STAGES][CH][REC]
-    uint64_t *sBar = reinterpret_cast<uint64_t *>(sRec + STAGES * CH * REC);   // full[STAGES], A
-    int *sCnt = reinterpret_cast<int *>(sBar + STAGES + 1);              // consumed[STAGES], flushed[2], done
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(sRec + STAGES * CH * REC);   // full[STAGES], A, flush[NFB]
+    uint64_t *barFlush = sBar + STAGES + 1;
+    int *sCnt = reinterpret_cast<int *>(barFlush + NFB);                 // consumed[STAGES]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int4 blk = P.sched[blockIdx.x];
@@ -196,7 +210,8 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
     if (tid < 32) sTab[tid] = c_exp2_tab[tid];
     if (tid == 0) {
         for (int s = 0; s <= STAGES; s++) mbar_init(&sBar[s], 1);
-        for (int s = 0; s < STAGES + 3; s++) sCnt[s] = 0;
+        for (int s = 0; s < NFB; s++) mbar_init(&barFlush[s], ntiles);     // one arrival per active warp and flush
+        for (int s = 0; s < STAGES; s++) sCnt[s] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -235,7 +250,58 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
     double out[NT];
 #pragma unroll
     for (int i = 0; i < NT; i++) out[i] = 0.0;
-    int flush_idx = 0;
+    int flush_idx = 0, J1 = 0, J2 = 0;      // J1 / J2: column groups of the previous two flushes
+
+    // Final sums of flush kk (column group J): every warp adds the per-warp partials of ITS share of the
+    // (row group, component) outputs in a fixed order and writes them.  Called two flushes later, when the
+    // partials of all warps have long been delivered (mbarrier per flush buffer; no atomics, no designated
+    // finisher warp, deterministic).  Buffer reuse is safe with NFB = 4: a warp overwrites buffer k & 3 at
+    // flush k only after it has seen flush k-2 complete, i.e. after every warp has summed its share of k-4.
+    auto finish = [&](int kk, int J) {
+        const int fb = kk & (NFB - 1);
+        mbar_wait(&barFlush[fb], (kk / NFB) & 1);
+        const int total = nent * NT;
+        for (int idx = lane * n_active + warp; idx < total; idx += 32 * n_active) {
+            const int en = idx / NT, o = idx - en * NT;
+            const int4 E4 = sEnt[en];
+            const int I = E4.x;
+            const double *src = sRow + (size_t)fb * MAXROWS * NT + o;
+            double v = src[E4.y * NT];
+            for (int r = (E4.y & ~7) + 8; r < E4.z; r += 8) v += src[r * NT];
+            const bool shared = E4.w != 0;
+            const bool isgrad = GRAD && o >= NOUT;
+            const int oo = isgrad ? o - NOUT : o;
+            if (FF) {
+                const int c = oo / 3, e = oo - 3 * c;
+                double *dst = isgrad ? P.dK : P.K;
+                const long long ld = isgrad ? P.lddk : P.ldk;
+                if (P.mode == GPRB_FF_DIAG) {
+                    if (I == J && c == e) {
+                        double *qd = dst + 3 * (I - P.grp_begin) + c;
+                        if (shared) atomicAdd(qd, v); else *qd = v;
+                    }
+                } else if (!((P.mode == GPRB_FF_SYMMETRIC || P.mode == GPRB_FF_UPPER) && J < I)) {
+                    double *qd = dst + (long long)(3 * (I - P.grp_begin) + c) * ld + 3 * J + e;
+                    if (shared) atomicAdd(qd, v); else *qd = v;
+                    if (P.mode == GPRB_FF_SYMMETRIC && J > I) {
+                        double *qt = dst + (long long)(3 * J + e) * ld + 3 * I + c;
+                        if (shared) atomicAdd(qt, v); else *qt = v;
+                    }
+                }
+            } else {
+                // a side = force group I (window), b side = energy group J; K_ef = -(1/n_J) sum
+                const int nJ = P.group_rowsB[J];
+                const double val = nJ > 0 ? -v / (double)nJ : 0.0;
+                const long long row = 3 * (I - P.grp_begin) + oo;
+                double *fe = isgrad ? P.dK : P.K;
+                const long long ldfe = isgrad ? P.lddk : P.ldk;
+                double *ef = isgrad ? P.dK2 : P.K2;
+                const long long ldef = isgrad ? P.lddk2 : P.ldk2;
+                if (fe) { double *qd = fe + row * ldfe + J; if (shared) atomicAdd(qd, val); else *qd = val; }
+                if (ef) { double *qd = ef + (long long)J * ldef + row; if (shared) atomicAdd(qd, val); else *qd = val; }
+            }
+        }
+    };
 
     mbar_wait(&sBar[STAGES], 0);         // row tiles have landed
     const double *pa = sA + (size_t)warp * a_tile_d + lane;
@@ -329,15 +395,8 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                 if (!(mf & 0x100)) continue;
 
                 // ---- flush: column group J is complete -------------------------------------------------
-                const int fb = flush_idx & 1;
-                if (flush_idx >= 2) {          // slot fb was used by flush_idx-2: wait until it has been summed
-                    if (lane == 0 && *reinterpret_cast<volatile int *>(&sCnt[STAGES + 2]) < flush_idx - 1) {
-                        const long long t0 = clock64();
-                        while (*reinterpret_cast<volatile int *>(&sCnt[STAGES + 2]) < flush_idx - 1)
-                            if (clock64() - t0 > SPIN_LIMIT_CYCLES) spin_timeout(2);
-                    }
-                    __syncwarp();
-                }
+                if (flush_idx >= 2) finish(flush_idx - 2, J2);      // my share of the sums of two flushes ago
+                const int fb = flush_idx & (NFB - 1);
                 const bool b0 = lane & 1, b1 = lane & 2;
                 double wv[N1], zv[N2];
 #pragma unroll
@@ -370,61 +429,8 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
 #pragma unroll
                 for (int i = 0; i < NT; i++) out[i] = 0.0;
                 __syncwarp();
-                int last = 0;
-                if (lane == 0) {
-                    __threadfence_block();
-                    last = ((atomicAdd(&sCnt[STAGES + fb], 1) + 1) % n_active) == 0;
-                }
-                last = __shfl_sync(0xffffffffu, last, 0);
-                if (last) {
-                    __threadfence_block();
-                    const int total = nent * NT;
-                    for (int idx = lane; idx < total; idx += 32) {
-                        const int en = idx / NT, o = idx - en * NT;
-                        const int4 E4 = sEnt[en];
-                        const int I = E4.x;
-                        const double *src = sRow + (size_t)fb * MAXROWS * NT + o;
-                        double v = src[E4.y * NT];
-                        for (int r = (E4.y & ~7) + 8; r < E4.z; r += 8) v += src[r * NT];
-                        const bool shared = E4.w != 0;
-                        const bool isgrad = GRAD && o >= NOUT;
-                        const int oo = isgrad ? o - NOUT : o;
-                        if (FF) {
-                            const int c = oo / 3, e = oo - 3 * c;
-                            double *dst = isgrad ? P.dK : P.K;
-                            const long long ld = isgrad ? P.lddk : P.ldk;
-                            if (P.mode == GPRB_FF_DIAG) {
-                                if (I == J && c == e) {
-                                    double *qd = dst + 3 * (I - P.grp_begin) + c;
-                                    if (shared) atomicAdd(qd, v); else *qd = v;
-                                }
-                            } else if (!((P.mode == GPRB_FF_SYMMETRIC || P.mode == GPRB_FF_UPPER) && J < I)) {
-                                double *qd = dst + (long long)(3 * (I - P.grp_begin) + c) * ld + 3 * J + e;
-                                if (shared) atomicAdd(qd, v); else *qd = v;
-                                if (P.mode == GPRB_FF_SYMMETRIC && J > I) {
-                                    double *qt = dst + (long long)(3 * J + e) * ld + 3 * I + c;
-                                    if (shared) atomicAdd(qt, v); else *qt = v;
-                                }
-                            }
-                        } else {
-                            // a side = force group I (window), b side = energy group J; K_ef = -(1/n_J) sum
-                            const int nJ = P.group_rowsB[J];
-                            const double val = nJ > 0 ? -v / (double)nJ : 0.0;
-                            const long long row = 3 * (I - P.grp_begin) + oo;
-                            double *fe = isgrad ? P.dK : P.K;
-                            const long long ldfe = isgrad ? P.lddk : P.ldk;
-                            double *ef = isgrad ? P.dK2 : P.K2;
-                            const long long ldef = isgrad ? P.lddk2 : P.ldk2;
-                            if (fe) { double *qd = fe + row * ldfe + J; if (shared) atomicAdd(qd, val); else *qd = val; }
-                            if (ef) { double *qd = ef + (long long)J * ldef + row; if (shared) atomicAdd(qd, val); else *qd = val; }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence_block();
-                        *reinterpret_cast<volatile int *>(&sCnt[STAGES + 2]) = flush_idx + 1;
-                    }
-                }
+                if (lane == 0) mbar_arrive(&barFlush[fb]);          // release: this warp's partials of flush k are in place
+                J2 = J1; J1 = J;
                 flush_idx++;
             }
         }
@@ -435,12 +441,15 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
             if ((old + 1) % n_active == 0 && ci + STAGES < c_end) issue(ci + STAGES, buf);
         }
     }
+    // the sums of the last two flushes
+    if (flush_idx >= 2) finish(flush_idx - 2, J2);
+    if (flush_idx >= 1) finish(flush_idx - 1, J1);
 }
 
 size_t cov_smem_bytes(int nb, int ks, bool grad) {
     const int nt = (nb == 4 ? 9 : 3) * (grad ? 2 : 1);
-    return (size_t)(WARPS * 4 * ks * 32 + STAGES * CH * nb * ks * 32 + 2 * MAXROWS * nt + 32) * 8 +
-           (size_t)MAXROWS * 16 + (size_t)STAGES * CH * REC * 4 + (STAGES + 1) * 8 + (STAGES + 3) * 4 + 128;
+    return (size_t)(WARPS * 4 * ks * 32 + STAGES * CH * nb * ks * 32 + NFB * MAXROWS * nt + 32) * 8 +
+           (size_t)MAXROWS * 16 + (size_t)STAGES * CH * REC * 4 + (STAGES + 1 + NFB) * 8 + STAGES * 4 + 128;
 }
 
 // Row-side schedule for the window [g0, g1): blocks of <= WARPS consecutive flat tiles and, per block, the
