@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-e2e", default=None, help="write a cProfile listing of one end-to-end step to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,7 +197,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n_cpu = args.cpu_structures or 3
+        n_cpu = args.cpu_structures or 5
         gf, dt, kind, sample = run_cpu(n_cpu, nrep, seed0, args.steps, max(args.warmup, 0), threads)
         print(json.dumps({"impl": "reference", "metric": "covariance_build_gflops", "value": gf, "unit": "GFLOP/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -234,7 +235,10 @@ def main():
     p_ef = e_pack.pair_count(f_pack)                                  # one pass writes K_ef and K_fe
     flops = flops_of(p_ff, p_ef, p_ee)
     config.update({"N": N, "force_rows": int(F_dev[0].shape[0]), "energy_rows": int(E_dev[0].shape[0]),
-                   "pairs_ff_evaluated": p_ff, "parallelism": "row-block x%d" % world})
+                   "pairs_ff_evaluated": p_ff, "parallelism": "row-block x%d" % world,
+                   "gather": "none (1 GPU)" if world == 1 else
+                   ("fused into the K_fe/K_ff epilogue (NVLink peer stores, gprb_k*_multi)" if gdist.peer_gather_enabled()
+                    else "NCCL all-gather (GPRB_NO_PEER=1)")})
 
     gp = GP(kernel=RBF_mb(para=[SIGMA, ELL], zeta=ZETA), descriptor=des, noise_e=NOISE_E, noise_f=NOISE_F, log_file=None)
     gp.train_x = {"energy": e_pack, "force": f_pack}      # device-resident packs (gdev.packs_of passes Packs through)
@@ -267,7 +271,7 @@ def main():
     prof, _lib.PROFILE = _lib.PROFILE, None
     launches = lib.gprb_launch_count() - launches0
     ms_step = ev0.elapsed_time(ev1) / args.steps
-    kff_ms = [a.elapsed_time(b) for n, a, b in prof if n == "gprb_kff"]
+    kff_ms = [a.elapsed_time(b) for n, a, b, _ in prof if n in ("gprb_kff", "gprb_kff_multi")]
     kff_ms_avg = float(np.mean(kff_ms))
     t = torch.tensor([ms_step, kff_ms_avg], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -319,6 +323,21 @@ def main():
         res = None
         for _ in range(min(max(args.warmup, 0), 3)):
             res = e2e_step()
+        if args.profile_e2e and rank == 0:
+            import cProfile
+            import io
+            import pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            e2e_step()
+            torch.cuda.synchronize()
+            pr.disable()
+            buf = io.StringIO()
+            pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(40)
+            with open(args.profile_e2e, "w") as fh:
+                fh.write(buf.getvalue())
+        elif args.profile_e2e:
+            e2e_step()
         barrier()
         _lib.PROFILE = []
         t0 = time.perf_counter()
@@ -331,15 +350,18 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t[0])
-        parts = {}
-        for n, a, b in prof:
+        parts, host_parts = {}, {}
+        for n, a, b, h in prof:
             parts[n] = parts.get(n, 0.0) + a.elapsed_time(b) / args.steps
+            host_parts[n] = host_parts.get(n, 0.0) + h * 1e3 / args.steps
         lml, grad = res
         result["e2e"] = {"value": flops / dt * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
                          "d2h_bytes_per_step": 16 * 5, "ms_per_step": dt * 1e3,
                          "call": "GP.log_marginal_likelihood(theta, eval_gradient=True) from pinned host packed arrays",
                          "device_ms_by_entry_point": {k: round(v, 3) for k, v in sorted(parts.items())},
+                         "host_ms_inside_entry_point": {k: round(v, 3) for k, v in sorted(host_parts.items())},
                          "lml": float(lml), "lml_grad": [float(g) for g in grad]}
+        gp2.release_peer()
         del gp2
         gdev.clear_cache()
 
@@ -349,8 +371,9 @@ def main():
         try:
             gp._alpha_dev = None
             K, _, _ = gp._build_K(grad=False)
+            K = gp._own(K)
             gp._alpha_dev = gp._factor(K, NOISE_E, NOISE_F)
-            gp._L_dev, gp._Kinv_dev = K, None
+            gp._L_dev, gp._Kinv_dev = K, None            # (K is an owned copy, see below)
             gp.set_K_inv()
             n_test = 64
             tests = [a for a, _, _ in syn.structures(n_test, nrep, seed0 + 1000)]
@@ -380,13 +403,16 @@ def main():
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_cpu = args.cpu_structures or 3
+        n_cpu = args.cpu_structures or 8
         gf, dt, kind, sample = run_cpu(n_cpu, nrep, seed0, 1, 0, threads)
         result["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample,
                                   "seconds": dt}
+    if world > 1 and getattr(gp, "_peer", None) is None and gdist.peer_gather_enabled():
+        result["config"]["gather"] = "NCCL all-gather (peer mapping unavailable)"
     if rank == 0:
         print(json.dumps(result))
     if world > 1:
+        gp.release_peer()
         dist.destroy_process_group()
 
 

@@ -13,6 +13,7 @@ c_int_p = ctypes.POINTER(ctypes.c_int)
 
 RBF, DOT = 0, 1
 FF_FULL, FF_SYMMETRIC, FF_DIAG, FF_UPPER = 0, 1, 2, 3
+MAX_DST = 8          # GPRB_MAX_DST: matrices one gprb_k*_multi call stores into
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_LINALG = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); every symbol declared in include/gpr_b200.h
@@ -29,6 +30,15 @@ SIGNATURES = {
                          c_vp, c_ll, c_vp, c_ll, c_vp]),
     "gprb_kef": (c_int, [c_int, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_int,
                          c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp]),
+    "gprb_kff_multi": (c_int, [c_int, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_dbl, c_int, c_int, c_int,
+                               c_int, ctypes.POINTER(c_vp), c_ll, c_vp, c_ll, c_vp]),
+    "gprb_kfe_multi": (c_int, [c_int, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_int,
+                               c_int, ctypes.POINTER(c_vp), c_ll, c_vp, c_ll, c_vp]),
+    "gprb_peer_alloc": (c_int, [ctypes.POINTER(c_vp), ctypes.c_ulonglong]),
+    "gprb_peer_free": (c_int, [c_vp]),
+    "gprb_peer_export": (c_int, [c_vp, ctypes.c_char_p]),
+    "gprb_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "gprb_peer_close": (c_int, [c_vp]),
     "gprb_kee": (c_int, [c_int, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_int, c_vp, c_ll, c_vp, c_ll, c_vp]),
     "gprb_kee_diag": (c_int, [c_int, c_vp, c_dbl, c_dbl, c_dbl, c_vp, c_vp]),
     "gprb_add_noise": (c_int, [c_vp, c_ll, c_int, c_int, c_dbl, c_dbl, c_vp]),
@@ -88,7 +98,8 @@ def check(code):
 
 
 # Optional per-call device timing (bench.py): set PROFILE to a list and every call() appends
-# (name, start_event, end_event), CUDA events recorded on the current torch stream around the call.
+# (name, start_event, end_event, host_seconds_inside_the_call), CUDA events recorded on the current torch
+# stream around the call.
 PROFILE = None
 
 
@@ -96,9 +107,12 @@ def call(name, *args):
     if PROFILE is None:
         check(getattr(load(), name)(*args))
         return
+    import time
     import torch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t0 = time.perf_counter()
     check(getattr(load(), name)(*args))
+    t1 = time.perf_counter()
     e1.record()
-    PROFILE.append((name, e0, e1))
+    PROFILE.append((name, e0, e1, t1 - t0))

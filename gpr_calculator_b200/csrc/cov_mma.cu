@@ -55,6 +55,9 @@ struct CovParams {
     int zi, use_tol, mode, grp_begin;
     double *K; long long ldk; double *dK; long long lddk;     // kff: K / dK/dl ; kfe: Kfe / dKfe
     double *K2; long long ldk2; double *dK2; long long lddk2; // kfe only: Kef / dKef (transposed copies)
+    // fused all-gather (gprb_kff_multi / gprb_kfe_multi): every finished value of K is also stored into the
+    // same slab of n_extra peer matrices (NVLink peer stores, pointers from gprb_peer_open); dK stays local
+    double *Kx[GPRB_MAX_DST - 1]; int n_extra;
 };
 
 __constant__ double c_exp2_tab[32];    // 2^(j/32)
@@ -281,8 +284,14 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                         if (shared) atomicAdd(qd, v); else *qd = v;
                     }
                 } else if (!((P.mode == GPRB_FF_SYMMETRIC || P.mode == GPRB_FF_UPPER) && J < I)) {
-                    double *qd = dst + (long long)(3 * (I - P.grp_begin) + c) * ld + 3 * J + e;
+                    const long long off = (long long)(3 * (I - P.grp_begin) + c) * ld + 3 * J + e;
+                    double *qd = dst + off;
                     if (shared) atomicAdd(qd, v); else *qd = v;
+                    if (!isgrad) {
+#pragma unroll
+                        for (int p = 0; p < GPRB_MAX_DST - 1; p++)
+                            if (p < P.n_extra) { double *qp = P.Kx[p] + off; if (shared) atomicAdd(qp, v); else *qp = v; }
+                    }
                     if (P.mode == GPRB_FF_SYMMETRIC && J > I) {
                         double *qt = dst + (long long)(3 * J + e) * ld + 3 * I + c;
                         if (shared) atomicAdd(qt, v); else *qt = v;
@@ -297,7 +306,16 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                 const long long ldfe = isgrad ? P.lddk : P.ldk;
                 double *ef = isgrad ? P.dK2 : P.K2;
                 const long long ldef = isgrad ? P.lddk2 : P.ldk2;
-                if (fe) { double *qd = fe + row * ldfe + J; if (shared) atomicAdd(qd, val); else *qd = val; }
+                if (fe) {
+                    const long long off = row * ldfe + J;
+                    double *qd = fe + off;
+                    if (shared) atomicAdd(qd, val); else *qd = val;
+                    if (!isgrad) {
+#pragma unroll
+                        for (int p = 0; p < GPRB_MAX_DST - 1; p++)
+                            if (p < P.n_extra) { double *qp = P.Kx[p] + off; if (shared) atomicAdd(qp, val); else *qp = val; }
+                    }
+                }
                 if (ef) { double *qd = ef + (long long)J * ldef + row; if (shared) atomicAdd(qd, val); else *qd = val; }
             }
         }
@@ -569,11 +587,15 @@ int choose_splits(int n_blocks, int n_groupsB) {
 
 }  // namespace
 
-extern "C" int gprb_kff(int kernel, const gprb_pack *f1_, const gprb_pack *f2, double p0, double p1, double zeta,
-                        int use_tol, double tol, int mode, int grp_begin, int grp_end,
-                        double *K, long long ldk, double *dK, long long lddk, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+// n_dst > 1: K_dst[1..] are the same row slab in peer matrices (fused all-gather); the outputs are then NOT
+// zeroed here (every GPU zeroes its own matrix before the ranks synchronise, see dist.PeerMatrix)
+static int kff_impl(int kernel, const gprb_pack *f1_, const gprb_pack *f2, double p0, double p1, double zeta,
+                    int use_tol, double tol, int mode, int grp_begin, int grp_end,
+                    int n_dst, double *const *K_dst, long long ldk, double *dK, long long lddk, cudaStream_t st) {
     gprb_pack *f1 = const_cast<gprb_pack *>(f1_);
+    GPRB_REQUIRE(n_dst >= 1 && n_dst <= GPRB_MAX_DST && K_dst, "gprb_kff: need 1..%d destination matrices", GPRB_MAX_DST);
+    for (int p = 0; p < n_dst; p++) GPRB_REQUIRE(K_dst[p], "gprb_kff: NULL destination %d", p);
+    double *K = K_dst[0];
     GPRB_REQUIRE(f1 && f2 && K, "gprb_kff: NULL argument");
     GPRB_REQUIRE(f1->ncols == 3 && f2->ncols == 3, "gprb_kff: both sides must be force packs");
     GPRB_REQUIRE(f1->d == f2->d, "gprb_kff: descriptor length mismatch %d vs %d", f1->d, f2->d);
@@ -595,9 +617,10 @@ extern "C" int gprb_kff(int kernel, const gprb_pack *f1_, const gprb_pack *f2, d
     // combined with atomics (UPPER leaves the blocks left of the diagonal zero)
     const int rows = 3 * (grp_end - grp_begin);
     if (mode == GPRB_FF_DIAG) {
+        GPRB_REQUIRE(n_dst == 1, "gprb_kff_multi: diag mode has a single destination");
         GPRB_CUDA(cudaMemsetAsync(K, 0, (size_t)rows * sizeof(double), st));
     } else {
-        GPRB_CUDA(cudaMemset2DAsync(K, ldk * sizeof(double), 0, (size_t)3 * f2->n_groups * sizeof(double), rows, st));
+        if (n_dst == 1) GPRB_CUDA(cudaMemset2DAsync(K, ldk * sizeof(double), 0, (size_t)3 * f2->n_groups * sizeof(double), rows, st));
         if (dK) GPRB_CUDA(cudaMemset2DAsync(dK, lddk * sizeof(double), 0, (size_t)3 * f2->n_groups * sizeof(double), rows, st));
     }
     if (f1->sched_n == 0 || f2->n_rows == 0) return GPRB_OK;
@@ -610,16 +633,36 @@ extern "C" int gprb_kff(int kernel, const gprb_pack *f1_, const gprb_pack *f2, d
     P.win_r0 = f1->row_ptr[grp_begin]; P.win_r1 = f1->row_ptr[grp_end];
     P.tol = tol; P.use_tol = use_tol; P.mode = mode; P.grp_begin = grp_begin;
     P.K = K; P.ldk = ldk; P.dK = dK; P.lddk = lddk;
+    P.n_extra = n_dst - 1;
+    for (int p = 1; p < n_dst; p++) P.Kx[p - 1] = K_dst[p];
     P.n_splits = mode == GPRB_FF_DIAG ? 1 : choose_splits(f1->sched_n, f2->n_groups);
     return dispatch_cov<4>(kernel, dK != nullptr, P, f1->sched_n, st);
 }
 
-extern "C" int gprb_kef(int kernel, const gprb_pack *e, const gprb_pack *f_, double p0, double p1, double zeta,
-                        int grp_begin, int grp_end,
-                        double *Kef, long long ld_ef, double *Kfe, long long ld_fe,
-                        double *dKef, long long ld_def, double *dKfe, long long ld_dfe, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+extern "C" int gprb_kff(int kernel, const gprb_pack *f1, const gprb_pack *f2, double p0, double p1, double zeta,
+                        int use_tol, double tol, int mode, int grp_begin, int grp_end,
+                        double *K, long long ldk, double *dK, long long lddk, void *stream) {
+    GPRB_REQUIRE(K, "gprb_kff: NULL argument");
+    double *dst[1] = {K};
+    return kff_impl(kernel, f1, f2, p0, p1, zeta, use_tol, tol, mode, grp_begin, grp_end, 1, dst, ldk, dK, lddk, (cudaStream_t)stream);
+}
+
+extern "C" int gprb_kff_multi(int kernel, const gprb_pack *f1, const gprb_pack *f2, double p0, double p1, double zeta,
+                              int use_tol, double tol, int mode, int grp_begin, int grp_end,
+                              int n_dst, double *const *K_dst_host, long long ldk, double *dK, long long lddk, void *stream) {
+    GPRB_REQUIRE(mode == GPRB_FF_FULL || mode == GPRB_FF_UPPER, "gprb_kff_multi: mode must be FULL or UPPER");
+    return kff_impl(kernel, f1, f2, p0, p1, zeta, use_tol, tol, mode, grp_begin, grp_end, n_dst, K_dst_host, ldk, dK, lddk,
+                    (cudaStream_t)stream);
+}
+
+static int kef_impl(int kernel, const gprb_pack *e, const gprb_pack *f_, double p0, double p1, double zeta,
+                    int grp_begin, int grp_end,
+                    double *Kef, long long ld_ef, int n_dst, double *const *Kfe_dst, long long ld_fe,
+                    double *dKef, long long ld_def, double *dKfe, long long ld_dfe, cudaStream_t st) {
     gprb_pack *f = const_cast<gprb_pack *>(f_);
+    GPRB_REQUIRE(n_dst >= 1 && n_dst <= GPRB_MAX_DST && Kfe_dst, "gprb_kef: need 1..%d destination matrices", GPRB_MAX_DST);
+    double *Kfe = Kfe_dst[0];
+    for (int p = 1; p < n_dst; p++) GPRB_REQUIRE(Kfe_dst[p], "gprb_kfe_multi: NULL destination %d", p);
     GPRB_REQUIRE(e && f && (Kef || Kfe), "gprb_kef: NULL argument");
     GPRB_REQUIRE(e->ncols == 0 && f->ncols == 3, "gprb_kef: need (energy pack, force pack)");
     GPRB_REQUIRE(e->d == f->d, "gprb_kef: descriptor length mismatch %d vs %d", e->d, f->d);
@@ -637,7 +680,7 @@ extern "C" int gprb_kef(int kernel, const gprb_pack *e, const gprb_pack *f_, dou
     const int rows = 3 * (grp_end - grp_begin);
     {
         const size_t w = (size_t)e->n_groups * sizeof(double);
-        if (Kfe) GPRB_CUDA(cudaMemset2DAsync(Kfe, ld_fe * sizeof(double), 0, w, rows, st));
+        if (Kfe && n_dst == 1) GPRB_CUDA(cudaMemset2DAsync(Kfe, ld_fe * sizeof(double), 0, w, rows, st));
         if (dKfe) GPRB_CUDA(cudaMemset2DAsync(dKfe, ld_dfe * sizeof(double), 0, w, rows, st));
         if (Kef) GPRB_CUDA(cudaMemset2DAsync(Kef, ld_ef * sizeof(double), 0, (size_t)rows * sizeof(double), e->n_groups, st));
         if (dKef) GPRB_CUDA(cudaMemset2DAsync(dKef, ld_def * sizeof(double), 0, (size_t)rows * sizeof(double), e->n_groups, st));
@@ -653,6 +696,25 @@ extern "C" int gprb_kef(int kernel, const gprb_pack *e, const gprb_pack *f_, dou
     P.mode = GPRB_FF_FULL; P.grp_begin = grp_begin;
     P.K = Kfe; P.ldk = ld_fe; P.dK = dKfe; P.lddk = ld_dfe;
     P.K2 = Kef; P.ldk2 = ld_ef; P.dK2 = dKef; P.lddk2 = ld_def;
+    P.n_extra = n_dst - 1;
+    for (int p = 1; p < n_dst; p++) P.Kx[p - 1] = Kfe_dst[p];
     P.n_splits = choose_splits(f->sched_n, e->n_groups);
     return dispatch_cov<1>(kernel, grad, P, f->sched_n, st);
+}
+
+extern "C" int gprb_kef(int kernel, const gprb_pack *e, const gprb_pack *f, double p0, double p1, double zeta,
+                        int grp_begin, int grp_end,
+                        double *Kef, long long ld_ef, double *Kfe, long long ld_fe,
+                        double *dKef, long long ld_def, double *dKfe, long long ld_dfe, void *stream) {
+    double *dst[1] = {Kfe};
+    return kef_impl(kernel, e, f, p0, p1, zeta, grp_begin, grp_end, Kef, ld_ef, 1, dst, ld_fe, dKef, ld_def, dKfe, ld_dfe,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int gprb_kfe_multi(int kernel, const gprb_pack *e, const gprb_pack *f, double p0, double p1, double zeta,
+                              int grp_begin, int grp_end, int n_dst, double *const *Kfe_dst_host, long long ld_fe,
+                              double *dKfe, long long ld_dfe, void *stream) {
+    GPRB_REQUIRE(Kfe_dst_host && n_dst >= 1 && Kfe_dst_host[0], "gprb_kfe_multi: NULL destination");
+    return kef_impl(kernel, e, f, p0, p1, zeta, grp_begin, grp_end, nullptr, 0, n_dst, Kfe_dst_host, ld_fe, nullptr, 0, dKfe, ld_dfe,
+                    (cudaStream_t)stream);
 }

@@ -271,12 +271,15 @@ def build_energy_rows(kernel, p0, p1, zeta, side1, side2, window, K, dK=None, ze
 
 
 def build_force_rows(kernel, p0, p1, zeta, side1, side2, window, K, dK=None, use_tol=True, tol=1e-10,
-                     zeta_ef=None, zeta_ff=None, ff_mode=_lib.FF_FULL, skip_kfe=False):
+                     zeta_ef=None, zeta_ff=None, ff_mode=_lib.FF_FULL, skip_kfe=False, peer_slabs=None):
     """Rows of side-1 force groups [fa, fb): K[:, :NE2] = K_fe, K[:, NE2:] = K_ff.
 
     K / dK: [3 (fb - fa), NE2 + 3 NF2] row-major views.  ff_mode: FF_FULL, FF_SYMMETRIC (side1 is
     side2, full window, mirrored entries written) or FF_UPPER (side1 is side2: only blocks J >= I
-    are written; finish with gprb_symmetrize)."""
+    are written; finish with gprb_symmetrize).
+    peer_slabs: device addresses of the same row slab (element (0, 0) of `K`) in the other ranks' copies of
+    the matrix (dist.PeerMatrix): the kernels store every finished value into all copies (fused gather,
+    gprb_kff_multi / gprb_kfe_multi); K is then NOT zeroed by the call, the caller has zeroed every copy."""
     _, f1 = side1
     e2, f2 = side2
     NE2, NF2 = _sizes(side2)
@@ -288,6 +291,20 @@ def build_force_rows(kernel, p0, p1, zeta, side1, side2, window, K, dK=None, use
     st = stream()
     ld = K.stride(0)
     ldd = dK.stride(0) if dK is not None else 0
+    if peer_slabs:
+        n_dst = 1 + len(peer_slabs)
+        if n_dst > _lib.MAX_DST:
+            raise ValueError("at most %d destination matrices" % _lib.MAX_DST)
+        base = K.data_ptr()
+        if e2 is not None and not skip_kfe:
+            dst = (c_vp * n_dst)(base, *[int(q) for q in peer_slabs])
+            _lib.call("gprb_kfe_multi", kernel, e2.handle, f1.handle, p0, p1, float(zeta_ef), fa, fb,
+                      n_dst, dst, ld, _at(dK, 0, 0), ldd, st)
+        if f2 is not None:
+            dst = (c_vp * n_dst)(base + NE2 * 8, *[int(q) + NE2 * 8 for q in peer_slabs])
+            _lib.call("gprb_kff_multi", kernel, f1.handle, f2.handle, p0, p1, float(zeta_ff), int(bool(use_tol)), float(tol),
+                      ff_mode, fa, fb, n_dst, dst, ld, _at(dK, 0, NE2), ldd, st)
+        return
     if e2 is not None and not skip_kfe:
         _lib.call("gprb_kef", kernel, e2.handle, f1.handle, p0, p1, float(zeta_ef), fa, fb,
                   c_vp(0), 0, _at(K, 0, 0), ld, c_vp(0), 0, _at(dK, 0, 0), ldd, st)

@@ -6,7 +6,15 @@ vstacks and broadcasts (RBF_mb.py:471-521, gaussianprocess.py:246-247,305-306) â
   * one in-place all-gather of the slabs into the full K on every GPU,
   * dK/dtheta never gathered: each rank traces its own rows, scalars are all-reduced.
 With the gloo backend (CPU tensors) the same partition / gather logic is exercised in the tests.
+
+On one NVLink / NVSwitch node the gather is fused into the covariance kernels instead (PeerMatrix): every
+rank's copy of K is mapped into every other process, the kernel epilogue stores each finished value into all
+copies, and two stream-ordered rank barriers replace the all-gather.
 """
+import ctypes
+import os
+import warnings
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -124,3 +132,111 @@ def all_reduce_sum(values, device="cpu", group=None):
     t = torch.tensor(list(values), dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return [float(v) for v in t.cpu()]
+
+
+# ------------------------------------------------------------------------------------------------
+# fused gather: K of every rank mapped into every process (CUDA IPC over NVLink peer access)
+# ------------------------------------------------------------------------------------------------
+class _RawDeviceArray:
+    """Device memory owned by libgpr_b200 (gprb_peer_alloc) exposed through __cuda_array_interface__ so
+    that torch can view it (torch stays the owner of streams and the tensor algebra around it)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def slab_pointers(bases, row0, col0, ld, itemsize=8):
+    """Pointer to element (row0, col0) of the same row-major matrix at each base address."""
+    return [int(b) + (int(row0) * int(ld) + int(col0)) * itemsize for b in bases]
+
+
+class PeerMatrix:
+    """An [N, N] float64 matrix per rank, every rank's copy mapped into every other process.
+
+    `tensor` is this rank's copy; `ptrs[r]` is the device address of rank r's copy as seen from this
+    process (ptrs[rank] is the local one).  Writers store into all copies (gprb_kff_multi /
+    gprb_kfe_multi); `barrier()` is a stream-ordered rank barrier (a one-element all-reduce on the current
+    stream): work enqueued after it on any rank starts after the work enqueued before it on every rank.
+    Collective: every rank of the group must construct / close it together."""
+
+    def __init__(self, N, group=None):
+        from . import _lib
+        rank, size = world()
+        self.N, self.rank, self.size, self.group = int(N), rank, size, group
+        self.ptrs, self._opened, self._local = [], [], ctypes.c_void_p(0)
+        nbytes = self.N * self.N * 8
+        _lib.call("gprb_peer_alloc", ctypes.byref(self._local), ctypes.c_ulonglong(nbytes))
+        try:
+            handle = ctypes.create_string_buffer(64)
+            _lib.call("gprb_peer_export", self._local, handle)
+            mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda()
+            every = torch.empty(size * 64, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = bytes(every.cpu().numpy().tobytes())
+            ok, err = 1, ""
+            ptrs = []
+            for r in range(size):
+                if r == rank:
+                    ptrs.append(int(self._local.value))
+                    continue
+                q = ctypes.c_void_p(0)
+                try:
+                    _lib.call("gprb_peer_open", every[64 * r:64 * (r + 1)], ctypes.byref(q))
+                    self._opened.append(q)
+                    ptrs.append(int(q.value))
+                except _lib.GprB200Error as exc:      # no peer access to that GPU (not one NVLink node?)
+                    ok, err = 0, str(exc)
+                    ptrs.append(0)
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                raise RuntimeError("peer mapping of K failed on at least one rank %s" % err)
+        except Exception:
+            self._release()
+            raise
+        self.ptrs = ptrs
+        self.tensor = torch.as_tensor(_RawDeviceArray(self._local.value, (self.N, self.N)), device="cuda")
+        self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def barrier(self):
+        dist.all_reduce(self._token, group=self.group)
+
+    def _release(self):
+        from . import _lib
+        lib = _lib.load()
+        for q in self._opened:
+            lib.gprb_peer_close(q)
+        self._opened = []
+        if self._local:
+            lib.gprb_peer_free(self._local)
+            self._local = ctypes.c_void_p(0)
+        self.ptrs = []
+
+    def close(self):
+        """Collective: nobody may still be writing into anybody's copy."""
+        if self._local:
+            self.barrier()
+            torch.cuda.synchronize()
+            self.tensor = None
+            for q in self._opened:          # unmap the peers' copies first, then everyone frees its own
+                from . import _lib
+                _lib.load().gprb_peer_close(q)
+            self._opened = []
+            self.barrier()
+            torch.cuda.synchronize()
+            self._release()
+
+
+def peer_gather_enabled():
+    """The fused gather is used for multi-GPU builds unless GPRB_NO_PEER=1 (then: NCCL all-gather)."""
+    return os.environ.get("GPRB_NO_PEER", "0") in ("", "0")
+
+
+def make_peer_matrix(N, group=None):
+    """PeerMatrix or None (with a warning) when the ranks cannot map each other's memory."""
+    try:
+        return PeerMatrix(N, group=group)
+    except Exception as exc:      # same outcome on every rank (the success flag is all-reduced)
+        warnings.warn("fused peer gather unavailable, using the NCCL all-gather: %s" % exc)
+        return None

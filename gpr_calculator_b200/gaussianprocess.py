@@ -36,6 +36,20 @@ from .utilities import (atomic_numbers, convert_train_data, force_rows, list_to_
                         tuple_to_list)
 
 
+def _zero_build_targets(K, NE, chunks=16):
+    """Zero what a row-sharded upper-triangle build accumulates into: the K_fe columns and the part of the
+    force-force block on and right of the diagonal (in `chunks` row bands; everything else is overwritten by the
+    mirror / transpose / K_ee copies that follow)."""
+    N = K.shape[0]
+    if N <= NE:
+        return
+    if NE:
+        K[NE:, :NE].zero_()
+    per = 3 * max(1, -(-((N - NE) // 3) // chunks))
+    for r in range(NE, N, per):
+        K[r:r + per, r:].zero_()
+
+
 def _lazy_SO3():
     from .SO3 import SO3
     return SO3
@@ -194,18 +208,39 @@ class GP():
         windows = gdist.row_windows(e.indices if e is not None else [], f_rows, size, upper=True, speed=speed)
         (e0, e1), (f0, f1) = windows[rank]
         n_loc = (e1 - e0) + 3 * (f1 - f0)
-        K = torch.empty((N, N), dtype=F64, device="cuda")
+        peer = self._peer_matrix(N)
+        K = peer.tensor if peer is not None else torch.empty((N, N), dtype=F64, device="cuda")
         dK = torch.zeros((n_loc, N), dtype=F64, device="cuda") if has_dk else None
         ff = dict(use_tol=args.pop("use_tol"), tol=args.pop("tol"), zeta_ff=args.pop("zeta_ff"))
-        # energy rows: K_ee only; K_ef is the transpose of the K_fe rows the force windows produce
-        build_energy_rows(side1=(e, f), side2=(e, f), window=(e0, e1), K=K[e0:e1],
-                          dK=None if dK is None else dK[:e1 - e0], skip_kef=True, **args)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        build_force_rows(side1=(e, f), side2=(e, f), window=(f0, f1), K=K[NE + 3 * f0:NE + 3 * f1],
-                         dK=None if dK is None else dK[e1 - e0:], ff_mode=_lib.FF_UPPER, **args, **ff)
-        t1.record()
-        gdist.gather_rows_inplace(K, windows, NE)
+        if peer is not None:
+            # Fused gather (replaces the gather + bcast of RBF_mb.py:471-521): the K_fe / K_ff kernels store
+            # every finished value into all ranks' copies of K over NVLink.  Every rank zeroes its own copy,
+            # barrier (nobody still uses the previous K, all copies are zero), build, barrier (all stores landed).
+            _zero_build_targets(K, NE)
+            peer.barrier()
+            Kee = torch.empty((NE, NE), dtype=F64, device="cuda")      # K_ee is small: NCCL gather of its row slabs
+            build_energy_rows(side1=(e, f), side2=(e, f), window=(e0, e1), K=Kee[e0:e1],
+                              dK=None if dK is None else dK[:e1 - e0], skip_kef=True, **args)
+            t0.record()
+            r0 = NE + 3 * f0
+            slabs = [q for r, q in enumerate(gdist.slab_pointers(peer.ptrs, r0, 0, N)) if r != rank]
+            build_force_rows(side1=(e, f), side2=(e, f), window=(f0, f1), K=K[r0:NE + 3 * f1],
+                             dK=None if dK is None else dK[e1 - e0:], ff_mode=_lib.FF_UPPER, peer_slabs=slabs, **args, **ff)
+            t1.record()
+            if NE:
+                gdist.gather_rows_inplace(Kee, [(w[0], (0, 0)) for w in windows], NE)
+                K[:NE, :NE] = Kee
+            peer.barrier()
+        else:
+            # energy rows: K_ee only; K_ef is the transpose of the K_fe rows the force windows produce
+            build_energy_rows(side1=(e, f), side2=(e, f), window=(e0, e1), K=K[e0:e1],
+                              dK=None if dK is None else dK[:e1 - e0], skip_kef=True, **args)
+            t0.record()
+            build_force_rows(side1=(e, f), side2=(e, f), window=(f0, f1), K=K[NE + 3 * f0:NE + 3 * f1],
+                             dK=None if dK is None else dK[e1 - e0:], ff_mode=_lib.FF_UPPER, **args, **ff)
+            t1.record()
+            gdist.gather_rows_inplace(K, windows, NE)
         st = stream()
         if NF:
             _lib.call("gprb_symmetrize", c_vp(K.data_ptr() + (NE * N + NE) * 8), N, 3 * NF, st)
@@ -224,6 +259,36 @@ class GP():
                 print("[shard] rank %d window %d:%d kff %.1f ms speed %s" % (rank, f0, f1, t0.elapsed_time(t1),
                                                                           np.round(self._shard_speed, 4)), flush=True)
         return K, dK, [(e0, e1), (NE + 3 * f0, NE + 3 * f1)]
+
+    def _peer_matrix(self, N):
+        """This rank's peer-mapped copy of K for the fused gather (dist.PeerMatrix), or None: one is kept per
+        GP and re-made (collectively) when the training set changes size."""
+        rank, size = gdist.world()
+        if size == 1 or size > _lib.MAX_DST or not gdist.peer_gather_enabled() or getattr(self, "_peer_failed", False):
+            return None
+        peer = getattr(self, "_peer", None)
+        if peer is not None and peer.N != N:
+            peer.close()
+            peer = self._peer = None
+        if peer is None:
+            peer = self._peer = gdist.make_peer_matrix(N)
+            if peer is None:
+                self._peer_failed = True
+        return peer
+
+    def release_peer(self):
+        """Collective: free the peer-mapped copy of K (every rank must call it)."""
+        peer = getattr(self, "_peer", None)
+        if peer is not None:
+            peer.close()
+            self._peer = None
+
+    def _own(self, K):
+        """A matrix the GP may keep: the peer-mapped K is overwritten by the next build, so copy out of it."""
+        peer = getattr(self, "_peer", None)
+        if peer is not None and peer.tensor is not None and K.data_ptr() == peer.tensor.data_ptr():
+            return K.clone()
+        return K
 
     def _factor(self, K, noise_e, noise_f):
         """K += noise; in-place Cholesky; alpha = K^-1 y.  Returns alpha (device vector)."""
@@ -377,6 +442,7 @@ class GP():
 
         # final covariance with the pair-cut variant of K_ff (f_tol = 1e-10), as k_total at :286
         K, _, _ = self._build_K(grad=False)
+        K = self._own(K)
         self._alpha_dev = self._factor(K, self.noise_e, self.noise_f)
         self._L_dev = K
         self.logging.info("Cholesky Decomp is Complete")

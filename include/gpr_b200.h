@@ -92,6 +92,37 @@ int gprb_kef(int kernel, const gprb_pack *e, const gprb_pack *f, double p0, doub
              double *Kef_dev, long long ld_ef, double *Kfe_dev, long long ld_fe,
              double *dKef_dev, long long ld_def, double *dKfe_dev, long long ld_dfe, void *stream);
 
+/* ---- row-sharded build with the all-gather fused into the epilogue ------------------------------
+ * The reference gathers the row slabs of every MPI rank as pickles on rank 0, vstacks them and
+ * broadcasts the result (RBF_mb.py:471-521, gaussianprocess.py:246-247, 305-306).  Here the GPU that
+ * owns a row block stores every finished value straight into the same slab of ALL copies of K:
+ * K_dst_host[0] is the slab in this GPU's matrix, K_dst_host[1..n_dst) the same slab in the peers'
+ * matrices (device pointers mapped with gprb_peer_open; NVLink peer stores / fp64 reductions issued by
+ * the kernel epilogue, overlapped with the DMMAs of the following column groups).  dK stays local.
+ * Unlike gprb_kff / gprb_kef the K destinations are NOT zeroed by the call (a GPU cannot order a memset
+ * of a peer's matrix against that peer's other writers): every GPU zeroes its own matrix, the ranks
+ * synchronise, then build; they synchronise again before anyone reads K.
+ * gprb_kff_multi: mode GPRB_FF_FULL or GPRB_FF_UPPER.  gprb_kfe_multi: the K_fe rows of the force
+ * window (K_fe[(3(J-grp_begin)+c)*ld_fe + I]). */
+#define GPRB_MAX_DST 8
+int gprb_kff_multi(int kernel, const gprb_pack *f1, const gprb_pack *f2, double p0, double p1, double zeta,
+                   int use_tol, double tol, int mode, int grp_begin, int grp_end,
+                   int n_dst, double *const *K_dst_host, long long ldk, double *dK_dev, long long lddk, void *stream);
+int gprb_kfe_multi(int kernel, const gprb_pack *e, const gprb_pack *f, double p0, double p1, double zeta,
+                   int grp_begin, int grp_end, int n_dst, double *const *Kfe_dst_host, long long ld_fe,
+                   double *dKfe_dev, long long ld_dfe, void *stream);
+
+/* Peer-visible device memory for the fused gather (one process per GPU on one NVLink / NVSwitch node).
+ * gprb_peer_alloc: cudaMalloc on the current device.  gprb_peer_export: 64-byte CUDA IPC handle to hand to
+ * the other processes (any transport; dist.py uses torch.distributed).  gprb_peer_open: map another
+ * process's allocation into this one with peer access enabled; the pointer is valid for kernels on the
+ * current device.  gprb_peer_close / gprb_peer_free undo them. */
+int gprb_peer_alloc(void **ptr_dev, unsigned long long bytes);
+int gprb_peer_free(void *ptr_dev);
+int gprb_peer_export(void *ptr_dev, unsigned char *handle64_host);
+int gprb_peer_open(const unsigned char *handle64_host, void **ptr_dev);
+int gprb_peer_close(void *ptr_dev);
+
 /* gprb_kee : energy-energy block K[(I-grp_begin)*ldk + J].  Replaces rbf_kee_many / _with_grad
  *            (rbf_kernel.cpp:5-98), dot_kee_many (dot_kernel.cpp:5-56), kee_C. */
 int gprb_kee(int kernel, const gprb_pack *e1, const gprb_pack *e2, double p0, double p1, double zeta,
