@@ -238,8 +238,6 @@ class SO3:
                         dtype=np.int32).reshape(S, 3)
         numbers = np.concatenate([np.asarray(s.numbers, dtype=np.int32) for s in structures]) if A else np.zeros(0, np.int32)
         struct_of = np.repeat(np.arange(S, dtype=np.int32), counts)
-        if self.weight_on:
-            raise NotImplementedError("weight_on=True is not supported by the device kernels yet")
 
         dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device="cuda")  # noqa: E731
         t_atom_ptr, t_struct_of = dev(atom_ptr, torch.int32), dev(struct_of, torch.int32)
@@ -274,7 +272,8 @@ class SO3:
             inv_vol = dev(1.0 / np.abs(np.linalg.det(cells.reshape(S, 3, 3))), torch.float64)
         _lib.call("gprb_so3_power", A, ptr(nb_ptr), ptr(nb_j), ptr(nb_rvec), ptr(rad), ptr(t_num), ptr(t_atom_ptr),
                   ptr(t_struct_of), ptr(seq_ptr), self.nmax, self.lmax, float(self.alpha), float(self.rcut), ptr(norm),
-                  1 if self.derivative else 0, ptr(x), ptr(dxdr), ptr(seq), ptr(t_pos), ptr(inv_vol), ptr(rdxdr), st)
+                  (1 if self.derivative else 0) | (2 if self.weight_on else 0), ptr(x), ptr(dxdr), ptr(seq), ptr(t_pos),
+                  ptr(inv_vol), ptr(rdxdr), st)
         if not to_host:
             return {'x': x, 'dxdr': dxdr, 'rdxdr': rdxdr, 'seq': seq, 'atom_ptr': t_atom_ptr, 'seq_ptr': seq_ptr,
                     'numbers': t_num, 'n_neighbors': n_nb}
@@ -302,9 +301,23 @@ class SO3:
 
         Args:
             atoms: an ASE-like atoms object (positions, cell, pbc, numbers, symbols)
-            atom_ids: must be None (all atoms), as everywhere in the reference's own callers
+            atom_ids: centre atoms to evaluate (None = all).  As in build_neighbor_list (SO3.py:354-401) the rows of
+                      the other atoms stay zero in x, and seq / dxdr / rdxdr hold the (i, j) rows of the requested
+                      centres only, in the order the ids are given.
             use_mpi: ignored; the device pass replaces the MPI split of SO3.py:228-296
         '''
-        if atom_ids is not None:
-            raise NotImplementedError("atom_ids subsets are not supported by the device descriptor")
-        return self.calculate_batch([atoms], to_host=True)[0]
+        out = self.calculate_batch([atoms], to_host=True)[0]
+        if atom_ids is None:
+            return out
+        ids = [int(i) for i in atom_ids]
+        x = np.zeros_like(out['x'])
+        x[ids] = out['x'][ids]
+        out['x'] = x
+        if self.derivative:
+            seq = out['seq']
+            rows = np.concatenate([np.flatnonzero(seq[:, 0] == i) for i in ids]) if ids else np.zeros(0, dtype=np.int64)
+            out['seq'] = seq[rows]
+            out['dxdr'] = out['dxdr'][rows]
+            if out.get('rdxdr') is not None:
+                out['rdxdr'] = out['rdxdr'][rows]
+        return out

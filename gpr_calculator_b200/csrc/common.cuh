@@ -12,6 +12,8 @@
 #define GPRB_EPS_NORM 1e-8         // rbf_kernel.cpp:10,26
 
 void gprb_set_error(const char *fmt, ...);
+int gprb_pool_init();            // stream-ordered pool of the current device, memory kept across synchronisations (pack.cu)
+void gprb_pool_free(void *ptr);  // cudaFreeAsync on the legacy default stream (NULL is fine)
 
 // kernels launched by this library so far (gprb_launch_count); bumped next to every <<< >>>
 #include <atomic>

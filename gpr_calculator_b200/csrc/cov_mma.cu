@@ -497,14 +497,14 @@ int build_sched(gprb_pack *a, int g0, int g1, cudaStream_t st) {
             if ((int)ents.size() > e0) blocks.push_back(make_int4(tb, nt, e0, (int)ents.size() - e0));
         }
     }
-    if (a->sched) { GPRB_CUDA(cudaFree(a->sched)); a->sched = nullptr; }
-    if (a->sched_ent) { GPRB_CUDA(cudaFree(a->sched_ent)); a->sched_ent = nullptr; }
+    if (a->sched) { GPRB_CUDA(cudaFreeAsync(a->sched, st)); a->sched = nullptr; }
+    if (a->sched_ent) { GPRB_CUDA(cudaFreeAsync(a->sched_ent, st)); a->sched_ent = nullptr; }
     a->sched_host = blocks; a->sched_ent_host = ents;
     a->sched_n = (int)blocks.size();
     a->sched_g0 = g0; a->sched_g1 = g1;
     if (!blocks.empty()) {
-        GPRB_CUDA(cudaMalloc((void **)&a->sched, blocks.size() * sizeof(int4)));
-        GPRB_CUDA(cudaMalloc((void **)&a->sched_ent, ents.size() * sizeof(int4)));
+        GPRB_CUDA(cudaMallocAsync((void **)&a->sched, blocks.size() * sizeof(int4), st));
+        GPRB_CUDA(cudaMallocAsync((void **)&a->sched_ent, ents.size() * sizeof(int4), st));
         GPRB_CUDA(cudaMemcpyAsync(a->sched, a->sched_host.data(), blocks.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
         GPRB_CUDA(cudaMemcpyAsync(a->sched_ent, a->sched_ent_host.data(), ents.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
     }

@@ -20,6 +20,7 @@ cusolverDnHandle_t g_solver = nullptr;
 cublasHandle_t g_blas = nullptr;
 
 int handles(cudaStream_t st) {
+    { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
     if (!g_solver) {
         if (cusolverDnCreate(&g_solver) != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnCreate failed"); return GPRB_ERR_CUDA; }
     }
@@ -273,6 +274,7 @@ extern "C" int gprb_lml_terms(const double *L, long long ldl, int N, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(L && y && alpha && out_host && N > 0, "gprb_lml_terms: bad argument");
     double *d = nullptr;
+    { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
     GPRB_CUDA(cudaMallocAsync((void **)&d, 2 * sizeof(double), st));
     lml_terms_kernel<<<1, 1024, 0, st>>>(L, ldl, N, y, alpha, d);
     GPRB_LAUNCHED();
@@ -291,6 +293,7 @@ extern "C" int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha, c
     if (r0 == r1) return GPRB_OK;
     const int blocks = (r1 - r0) < 1184 ? (r1 - r0) : 1184;   // 8 x 148
     double *d = nullptr;
+    { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
     GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
     trace_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, alpha, Kinv, ldi, dK_rows, lddk, NE, we, wf, upper_only, d);
     GPRB_LAUNCHED();
@@ -312,6 +315,7 @@ extern "C" int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const dou
     if (r0 == r1 || c0 == c1) return GPRB_OK;
     const int blocks = (r1 - r0) < 1184 ? (r1 - r0) : 1184;
     double *d = nullptr;
+    { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
     GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
     block_sum_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, c0, c1, alpha, Kinv, ldi, d);
     GPRB_LAUNCHED();

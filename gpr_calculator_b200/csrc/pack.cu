@@ -110,10 +110,34 @@ static int stage_input(const T *any, size_t count, const T **dev, T **owned, cud
     return GPRB_OK;
 }
 
+// All device memory of the library comes from the stream-ordered pool of the device with the release
+// threshold raised to "never": packs are created and destroyed on every training-set change and once per
+// predicted structure, and cudaMalloc / cudaFree (and a pool that hands its memory back to the OS at every
+// synchronisation) showed up as random 0.1 - 1 s host stalls in the end-to-end likelihood step.
+int gprb_pool_init() {
+    static bool done[64] = {};
+    int dev = 0;
+    GPRB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || done[dev]) return GPRB_OK;
+    cudaMemPool_t pool;
+    GPRB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long never = ~0ULL;
+    GPRB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+    done[dev] = true;
+    return GPRB_OK;
+}
+
+// Frees are ordered on the legacy default stream: it synchronises with every blocking stream, so work that
+// still reads the pack on another (blocking) stream completes first.
+void gprb_pool_free(void *ptr) {
+    if (ptr) cudaFreeAsync(ptr, (cudaStream_t)0);
+}
+
 extern "C" void gprb_pack_destroy(gprb_pack *p) {
     if (!p) return;
-    cudaFree(p->P); cudaFree(p->norm); cudaFree(p->elep); cudaFree(p->row_group); cudaFree(p->tile_rec);
-    cudaFree(p->d_row_ptr); cudaFree(p->d_group_rows); cudaFree(p->sched); cudaFree(p->sched_ent);
+    gprb_pool_free(p->P); gprb_pool_free(p->norm); gprb_pool_free(p->elep); gprb_pool_free(p->row_group);
+    gprb_pool_free(p->tile_rec); gprb_pool_free(p->d_row_ptr); gprb_pool_free(p->d_group_rows);
+    gprb_pool_free(p->sched); gprb_pool_free(p->sched_ent);
     delete p;
 }
 
@@ -127,6 +151,7 @@ extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_
     GPRB_REQUIRE(ncols == 0 || ncols == 3, "gprb_pack_create: ncols must be 0 (energy) or 3 (force), got %d", ncols);
     GPRB_REQUIRE(norm_eps >= 0.0, "gprb_pack_create: norm_eps must be >= 0");
     GPRB_REQUIRE(ncols == 0 || dxdr_any != nullptr || n_groups == 0, "gprb_pack_create: dxdr is NULL for a force pack");
+    { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
     gprb_pack *p = new gprb_pack();
     GPRB_CUDA(cudaGetDevice(&p->device));
     p->n_groups = n_groups; p->d = d; p->ncols = ncols; p->ncomp = 1 + ncols; p->ks = (d + 3) / 4;
@@ -167,13 +192,13 @@ extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_
 
     const size_t pbytes = (size_t)tiles * p->ncomp * p->ks * 32 * sizeof(double);
 #define PK_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { gprb_set_error("%s:%d CUDA error %s", __FILE__, __LINE__, cudaGetErrorString(_e)); gprb_pack_destroy(p); return GPRB_ERR_CUDA; } } while (0)
-    PK_CUDA(cudaMalloc((void **)&p->P, pbytes));
-    PK_CUDA(cudaMalloc((void **)&p->norm, (size_t)n_padded * sizeof(double)));
-    PK_CUDA(cudaMalloc((void **)&p->elep, (size_t)n_padded * sizeof(int)));
-    PK_CUDA(cudaMalloc((void **)&p->row_group, (size_t)n_padded * sizeof(int)));
-    PK_CUDA(cudaMalloc((void **)&p->tile_rec, rec.size() * sizeof(int)));
-    PK_CUDA(cudaMalloc((void **)&p->d_row_ptr, (size_t)(n_groups + 1) * sizeof(int)));
-    PK_CUDA(cudaMalloc((void **)&p->d_group_rows, (size_t)(n_groups > 0 ? n_groups : 1) * sizeof(int)));
+    PK_CUDA(cudaMallocAsync((void **)&p->P, pbytes, st));
+    PK_CUDA(cudaMallocAsync((void **)&p->norm, (size_t)n_padded * sizeof(double), st));
+    PK_CUDA(cudaMallocAsync((void **)&p->elep, (size_t)n_padded * sizeof(int), st));
+    PK_CUDA(cudaMallocAsync((void **)&p->row_group, (size_t)n_padded * sizeof(int), st));
+    PK_CUDA(cudaMallocAsync((void **)&p->tile_rec, rec.size() * sizeof(int), st));
+    PK_CUDA(cudaMallocAsync((void **)&p->d_row_ptr, (size_t)(n_groups + 1) * sizeof(int), st));
+    PK_CUDA(cudaMallocAsync((void **)&p->d_group_rows, (size_t)(n_groups > 0 ? n_groups : 1) * sizeof(int), st));
     PK_CUDA(cudaMemcpyAsync(p->row_group, rgroup.data(), (size_t)n_padded * sizeof(int), cudaMemcpyHostToDevice, st));
     PK_CUDA(cudaMemcpyAsync(p->tile_rec, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     PK_CUDA(cudaMemcpyAsync(p->d_row_ptr, p->row_ptr.data(), (size_t)(n_groups + 1) * sizeof(int), cudaMemcpyHostToDevice, st));

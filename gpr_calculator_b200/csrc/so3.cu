@@ -258,7 +258,9 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
             const double dfc = -0.5 * PI / p.rcut * sin(PI * r / p.rcut);
             sGeo[0] = r; sGeo[1] = rx / r; sGeo[2] = ry / r; sGeo[3] = rz / r;
             sGeo[4] = gauss; sGeo[5] = -2.0 * p.alpha * r * gauss; sGeo[6] = fc; sGeo[7] = dfc;
-            sGeo[8] = (double)a.numbers[a.nb_j[w]];
+            // neighbour weight Z_j; weight_on: a neighbour of another species counts negative (SO3.py:381-385)
+            const int zj = a.numbers[a.nb_j[w]];
+            sGeo[8] = ((a.derivative & 2) && zj != a.numbers[i]) ? -(double)zj : (double)zj;
         }
     };
 
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
         }
         a.x[(size_t)i * d + o] = s;
     }
-    if (!a.derivative) return;
+    if (!(a.derivative & 1)) return;
 
     // ---- phase B: dP per neighbour, grouped by neighbour atom j -----------------------------------
     int row = a.seq_ptr[i];
@@ -465,10 +467,10 @@ extern "C" int gprb_so3_power(int n_atoms, const int *nb_ptr, const int *nb_j, c
                               const double *pos, const double *inv_vol, double *rdxdr, void *stream) {
     if (n_atoms == 0) return GPRB_OK;
     GPRB_REQUIRE(nb_ptr && numbers && atom_ptr && struct_of && norm_l && x, "gprb_so3_power: NULL argument");
-    GPRB_REQUIRE(!derivative || (seq_ptr && dxdr && seq), "gprb_so3_power: derivative outputs missing");
+    GPRB_REQUIRE(!(derivative & 1) || (seq_ptr && dxdr && seq), "gprb_so3_power: derivative outputs missing");
     GPRB_REQUIRE(nmax >= 1 && lmax >= 0 && lmax <= SO3_MAXL - 1, "gprb_so3_power: need nmax >= 1 and 0 <= lmax <= %d", SO3_MAXL - 1);
     SO3Params p{nmax, lmax, 0, alpha, rcut, nullptr, nullptr, norm_l};
-    GPRB_REQUIRE(!rdxdr || (derivative && pos && inv_vol), "gprb_so3_power: stress output needs derivative, pos and inv_vol");
+    GPRB_REQUIRE(!rdxdr || ((derivative & 1) && pos && inv_vol), "gprb_so3_power: stress output needs derivative, pos and inv_vol");
     SO3Power a{nb_ptr, nb_j, nb_rvec, rad, numbers, atom_ptr, struct_of, seq_ptr, x, dxdr, seq, derivative, pos, inv_vol, rdxdr};
     const int L1 = lmax + 1, M = 2 * lmax + 1, LY = lmax + 1;
     const int nent = nmax * L1 * M, d = nmax * (nmax + 1) / 2 * L1;

@@ -191,6 +191,8 @@ int gprb_predict(int m, int N, const double *Ks_dev, long long ldks, const doubl
  *   nodes and the combined weights g_n(rho) rho^2 e^{-a rho^2} sqrt(1-t^2) w (SO3.py:633,646-647).
  * gprb_so3_power     : c_nlm, power spectrum x[n_atoms,d], dxdr[n_seq,d,3] and seq[n_seq,2] (int64,
  *   atom indices local to the structure) (SO3.py:243-273, 655-727); seq_ptr = exclusive scan of nuniq.
+ *   derivative: bit 0 = also dxdr / seq; bit 1 = weight_on (SO3.py:381-385: a neighbour whose species differs
+ *   from the centre's enters with weight -Z_j instead of Z_j).
  *   rdxdr != NULL (stress, SO3.py:253-273, 304-306): also rdxdr[n_seq,d,3,3] = -pstress / volume with
  *   pos[n_atoms,3] the atom positions and inv_vol[S] = 1 / cell volume of each structure. */
 int gprb_so3_neighbors(int n_struct, int n_atoms, const int *atom_ptr, const int *struct_of,

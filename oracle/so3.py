@@ -122,12 +122,15 @@ def expansion_coefficients(rvec, nmax, lmax, rcut, alpha):
     return C0 * fc[:, None, None, None], dC
 
 
-def so3_calculate(positions, cell, pbc, numbers, nmax=3, lmax=4, rcut=5.0, alpha=2.0, stress=False):
+def so3_calculate(positions, cell, pbc, numbers, nmax=3, lmax=4, rcut=5.0, alpha=2.0, stress=False, weight_on=False,
+                  atom_ids=None):
     """Power spectrum x [n, d], its derivative dxdr [n_seq, d, 3] and seq [n_seq, 2] (int64),
     with the reference's conventions (SO3.py:186-323): weights Z_j, norm_l, tril(n >= n') x l layout,
     dxdr[(i, j)] = dx_i/dr_j summed over images, dxdr[(i, i)] = - sum_{j != i}.
     stress=True also returns rdxdr [n_seq, d, 3, 3] = -pstress / volume (SO3.py:253-273, 304-306):
-    pstress[(i, j)] = -sum_w R_j(w) (x) dP(w), pstress[(i, i)] += R_i (x) sum_w dP(w)."""
+    pstress[(i, j)] = -sum_w R_j(w) (x) dP(w), pstress[(i, i)] += R_i (x) sum_w dP(w).
+    weight_on: a neighbour of another species than the centre weighs -Z_j (SO3.py:381-385).
+    atom_ids: centres to evaluate, in the given order (SO3.py:354-401); other rows of x stay zero."""
     positions = np.asarray(positions, float)
     numbers = np.asarray(numbers)
     n = len(positions)
@@ -139,7 +142,8 @@ def so3_calculate(positions, cell, pbc, numbers, nmax=3, lmax=4, rcut=5.0, alpha
     nb_sets = [set([i]) for i in range(n)]
     for (i, j, *_s) in pairs:
         nb_sets[i].add(j)
-    seq = np.array([[i, j] for i in range(n) for j in sorted(nb_sets[i])], dtype=np.int64).reshape(-1, 2)
+    centres = list(range(n)) if atom_ids is None else [int(i) for i in atom_ids]
+    seq = np.array([[i, j] for i in centres for j in sorted(nb_sets[i])], dtype=np.int64).reshape(-1, 2)
     row_of = {(int(a), int(b)): k for k, (a, b) in enumerate(seq)}
     x = np.zeros((n, d))
     dxdr = np.zeros((len(seq), d, 3))
@@ -155,9 +159,11 @@ def so3_calculate(positions, cell, pbc, numbers, nmax=3, lmax=4, rcut=5.0, alpha
     ls = np.arange(lmax + 1)
     norm = np.sqrt(2 * np.sqrt(2) * np.pi / np.sqrt(2 * ls + 1))
     wgt = numbers[pj].astype(float)
+    if weight_on:
+        wgt = np.where(numbers[pj] != numbers[pi], -wgt, wgt)
     C = C * wgt[:, None, None, None] * norm[None, None, :, None]
     dC = dC * wgt[:, None, None, None, None] * norm[None, None, :, None, None]
-    for i in range(n):
+    for i in centres:
         sel = np.nonzero(pi == i)[0]
         if len(sel) == 0:
             continue

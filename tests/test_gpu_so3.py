@@ -73,3 +73,22 @@ def test_so3_finite_difference():
     for (i, jj), row in zip(r["seq"], r["dxdr"]):
         if jj == j:
             assert np.abs(row[:, c] - fd[i]).max() <= 1e-6 * max(1.0, np.abs(fd[i]).max())
+
+
+def test_so3_options_vs_golden():
+    """SO3(weight_on=True), derivative=False and calculate(atom_ids=...) against the reference's own output."""
+    from gpr_calculator_b200.SO3 import SO3
+    from gpr_calculator_b200.utilities import SimpleAtoms
+    g = np.load(os.path.join(GOLD, "so3_options.npz"))
+    for k in range(2):
+        prm = g["s%d_prm" % k]
+        kw = dict(nmax=int(prm[0]), lmax=int(prm[1]), rcut=float(prm[2]), alpha=float(prm[3]))
+        at = SimpleAtoms(g["s%d_numbers" % k], g["s%d_pos" % k], g["s%d_cell" % k], g["s%d_pbc" % k])
+        r = SO3(weight_on=True, **kw).calculate(at)
+        assert np.array_equal(r["seq"], g["s%d_w_seq" % k])
+        assert rel_err(r["x"], g["s%d_w_x" % k]) <= 1e-10 and rel_err(r["dxdr"], g["s%d_w_dxdr" % k]) <= 1e-10
+        r = SO3(weight_on=True, derivative=False, **kw).calculate(at)
+        assert r["dxdr"] is None and rel_err(r["x"], g["s%d_nod_x" % k]) <= 1e-10
+        r = SO3(**kw).calculate(at, atom_ids=list(g["s%d_ids" % k]))
+        assert r["seq"].dtype == np.int64 and np.array_equal(r["seq"], g["s%d_sub_seq" % k])
+        assert rel_err(r["x"], g["s%d_sub_x" % k]) <= 1e-10 and rel_err(r["dxdr"], g["s%d_sub_dxdr" % k]) <= 1e-10

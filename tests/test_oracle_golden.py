@@ -165,3 +165,20 @@ def test_gp_oracle_matches_golden(oracle_libs):
     bound = std_tolerance(g["K_b"], 0.002, 0.1, 3, ker.diag(X))
     assert abs(std[0] ** 2 - g["pred_E_std"] ** 2) <= bound
     assert np.abs(std[1:].reshape(-1, 3) ** 2 - g["pred_F_std"][free] ** 2).max() <= bound
+
+
+def test_so3_oracle_options_match_golden():
+    """weight_on=True and calculate(atom_ids=...) of the reference (tests/golden/gen_golden_so3_options.py)."""
+    from oracle import so3 as oso3
+    g = np.load(os.path.join(GOLD, "so3_options.npz"))
+    for k in range(2):
+        prm = g["s%d_prm" % k]
+        args = (g["s%d_pos" % k], g["s%d_cell" % k], g["s%d_pbc" % k], g["s%d_numbers" % k],
+                int(prm[0]), int(prm[1]), float(prm[2]), float(prm[3]))
+        x, dxdr, seq = oso3.so3_calculate(*args, weight_on=True)
+        assert np.array_equal(seq, g["s%d_w_seq" % k])
+        assert rel_err(x, g["s%d_w_x" % k]) <= 1e-10 and rel_err(dxdr, g["s%d_w_dxdr" % k]) <= 1e-10
+        assert rel_err(x, g["s%d_nod_x" % k]) <= 1e-10
+        x, dxdr, seq = oso3.so3_calculate(*args, atom_ids=list(g["s%d_ids" % k]))
+        assert np.array_equal(seq, g["s%d_sub_seq" % k])
+        assert rel_err(x, g["s%d_sub_x" % k]) <= 1e-10 and rel_err(dxdr, g["s%d_sub_dxdr" % k]) <= 1e-10
