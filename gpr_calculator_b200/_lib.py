@@ -47,6 +47,9 @@ SIGNATURES = {
     "gprb_chol_inverse": (c_int, [c_vp, c_ll, c_int, c_vp, c_ll, c_vp]),
     "gprb_lml_terms": (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp]),
     "gprb_lml_grad_trace": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_ll, c_vp, c_ll, c_int, c_dbl, c_dbl, c_int, c_vp, c_vp]),
+    "gprb_chol_inverse_rows": (c_int, [c_vp, c_ll, c_int, c_int, c_int, c_int, c_vp, c_ll, c_vp]),
+    "gprb_lml_grad_trace_rows": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_ll, c_int, c_vp, c_ll, c_vp, c_ll,
+                                         c_int, c_dbl, c_dbl, c_vp, c_vp]),
     "gprb_symmetrize": (c_int, [c_vp, c_ll, c_int, c_vp]),
     "gprb_transpose_copy": (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_vp]),
     "gprb_fp64_dmma_peak": (c_int, [c_vp, c_vp]),

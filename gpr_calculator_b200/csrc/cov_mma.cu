@@ -167,7 +167,7 @@ __device__ __forceinline__ void pair_weights(const CovParams &P, const double *t
     }
 }
 
-template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI>
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI>
 __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) {
     constexpr bool FF = (NB == 4);
     constexpr int NOUT = FF ? 9 : 3;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                     const long long off = (long long)(3 * (I - P.grp_begin) + c) * ld + 3 * J + e;
                     double *qd = dst + off;
                     if (shared) atomicAdd(qd, v); else *qd = v;
-                    if (!isgrad) {
+                    if (MULTI && !isgrad) {
 #pragma unroll
                         for (int p = 0; p < GPRB_MAX_DST - 1; p++)
                             if (p < P.n_extra) { double *qp = P.Kx[p] + off; if (shared) atomicAdd(qp, v); else *qp = v; }
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                     const long long off = row * ldfe + J;
                     double *qd = fe + off;
                     if (shared) atomicAdd(qd, val); else *qd = val;
-                    if (!isgrad) {
+                    if (MULTI && !isgrad) {
 #pragma unroll
                         for (int p = 0; p < GPRB_MAX_DST - 1; p++)
                             if (p < P.n_extra) { double *qp = P.Kx[p] + off; if (shared) atomicAdd(qp, val); else *qp = val; }
@@ -526,9 +526,9 @@ int upload_tables() {
     return GPRB_OK;
 }
 
-template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI>
-int launch_cov(const CovParams &P, int n_blocks, cudaStream_t st) {
-    auto kern = cov_mma_kernel<NB, KS_T, KERNEL, GRAD, ZI>;
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI>
+int launch_cov_m(const CovParams &P, int n_blocks, cudaStream_t st) {
+    auto kern = cov_mma_kernel<NB, KS_T, KERNEL, GRAD, ZI, MULTI>;
     static bool configured = false;
     if (!configured) {
         GPRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_smem_bytes(NB, GPRB_MAX_KS, GRAD)));
@@ -539,6 +539,13 @@ int launch_cov(const CovParams &P, int n_blocks, cudaStream_t st) {
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
+}
+
+// the single-destination kernels carry no peer-store code at all (MULTI = false)
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI>
+int launch_cov(const CovParams &P, int n_blocks, cudaStream_t st) {
+    return P.n_extra > 0 ? launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, true>(P, n_blocks, st)
+                         : launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, false>(P, n_blocks, st);
 }
 
 template <int NB, int KS_T, int ZI>

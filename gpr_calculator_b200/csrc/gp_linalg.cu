@@ -10,6 +10,7 @@
 // All matrices are row-major; a symmetric row-major matrix is handed to the column-major libraries
 // unchanged, "lower" here == CUBLAS_FILL_MODE_UPPER there.
 #include "common.cuh"
+#include <cstdint>
 #include <cusolverDn.h>
 #include <cublas_v2.h>
 #include <cstdlib>
@@ -89,10 +90,13 @@ __global__ void lml_terms_kernel(const double *L, long long ld, int N, const dou
 
 // partial[block] = sum over the block's rows of sum_j (alpha_i alpha_j - Kinv_ij) * dK_ij
 // partial2[block] = sum over rows of (alpha_i^2 - Kinv_ii) * w_i
+// KinvE != NULL (sharded inverse, gprb_lml_grad_trace_rows): the columns j < NE of a force row come from the
+// energy rows of the inverse, Kinv[i, j] = KinvE[j * ldE + i]; Kinv then only has to be valid for j >= i.
 __global__ void __launch_bounds__(256) trace_kernel(int N, int r0, int r1, const double *__restrict__ alpha,
                                                     const double *__restrict__ Kinv, long long ldi,
                                                     const double *__restrict__ dK, long long lddk,
-                                                    int NE, double we, double wf, int upper_only, double *partial) {
+                                                    int NE, double we, double wf, int upper_only, double *partial,
+                                                    const double *__restrict__ KinvE = nullptr, long long ldE = 0) {
     __shared__ double sh[32];
     double acc = 0.0, acc2 = 0.0;
     for (int i = r0 + blockIdx.x; i < r1; i += gridDim.x) {
@@ -108,8 +112,12 @@ __global__ void __launch_bounds__(256) trace_kernel(int N, int r0, int r1, const
                     const double t = fma(ai, alpha[j], -ki[j]) * di[j];
                     acc += (j == i) ? t : 2.0 * t;
                 }
-                if (upper_only == 2 && i >= NE)
-                    for (int j = threadIdx.x; j < NE; j += blockDim.x) acc += 2.0 * fma(ai, alpha[j], -ki[j]) * di[j];
+                if (upper_only == 2 && i >= NE) {
+                    if (KinvE)
+                        for (int j = threadIdx.x; j < NE; j += blockDim.x) acc += 2.0 * fma(ai, alpha[j], -KinvE[(long long)j * ldE + i]) * di[j];
+                    else
+                        for (int j = threadIdx.x; j < NE; j += blockDim.x) acc += 2.0 * fma(ai, alpha[j], -ki[j]) * di[j];
+                }
             } else {
                 for (int j = threadIdx.x; j < N; j += blockDim.x) acc = fma(fma(ai, alpha[j], -ki[j]), di[j], acc);
             }
@@ -304,6 +312,63 @@ extern "C" int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha, c
     int rc = copy_scalars(out_host, d + 2 * blocks, 2, st);
     cudaFreeAsync(d, st);
     return rc;
+}
+
+extern "C" int gprb_lml_grad_trace_rows(int N, int r0, int r1, const double *alpha, const double *Kinv_rows, long long ldr,
+                                        int c0, const double *KinvE, long long ldE, const double *dK_rows, long long lddk,
+                                        int NE, double we, double wf, double *out_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(alpha && Kinv_rows && out_host && 0 <= r0 && r0 <= r1 && r1 <= N && 0 <= c0 && c0 <= r0,
+                 "gprb_lml_grad_trace_rows: bad argument");
+    GPRB_REQUIRE(KinvE || r1 <= NE || NE == 0 || c0 == 0, "gprb_lml_grad_trace_rows: force rows need the energy rows of the inverse");
+    out_host[0] = out_host[1] = 0.0;
+    if (r0 == r1) return GPRB_OK;
+    // the kernel indexes Kinv[i * ld + j] with global (i, j): shift the base so that (r0, c0) is element 0 of the slab
+    const double *virt = reinterpret_cast<const double *>(reinterpret_cast<uintptr_t>(Kinv_rows) -
+                                                          (uintptr_t)(((long long)r0 * ldr + c0) * (long long)sizeof(double)));
+    const int blocks = (r1 - r0) < 1184 ? (r1 - r0) : 1184;
+    double *d = nullptr;
+    { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
+    GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
+    trace_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, alpha, virt, ldr, dK_rows, lddk, NE, we, wf, 2, d, KinvE, ldE);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, d + 2 * blocks);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    int rc = copy_scalars(out_host, d + 2 * blocks, 2, st);
+    cudaFreeAsync(d, st);
+    return rc;
+}
+
+__global__ void unit_columns_kernel(double *B, long long ldb, int n_rows, int col0) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_rows) B[(long long)k * ldb + col0 + k] = 1.0;
+}
+
+extern "C" int gprb_chol_inverse_rows(const double *L, long long ldl, int N, int r0, int r1, int c0,
+                                      double *out, long long ldo, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(L && out && N > 0 && 0 <= c0 && c0 <= r0 && r0 <= r1 && r1 <= N && ldo >= N - c0,
+                 "gprb_chol_inverse_rows: bad argument");
+    if (r0 == r1) return GPRB_OK;
+    int rc = handles(st);
+    if (rc) return rc;
+    // K^-1[T, T] = (L_TT L_TT^T)^-1 for the trailing index set T = [c0, N) (L^-1 is triangular), so rows
+    // [r0, r1) of the inverse, restricted to the columns >= c0, are the solution of the trailing system with
+    // the unit vectors of those rows as right-hand sides (symmetric: row = column).
+    const int n = N - c0, nrhs = r1 - r0;
+    GPRB_CUDA(cudaMemset2DAsync(out, ldo * sizeof(double), 0, (size_t)n * sizeof(double), nrhs, st));
+    unit_columns_kernel<<<(nrhs + 255) / 256, 256, 0, st>>>(out, ldo, nrhs, r0 - c0);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    int *info = nullptr;
+    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
+    cusolverStatus_t cs = cusolverDnDpotrs(g_solver, CUBLAS_FILL_MODE_UPPER, n, nrhs, L + (long long)c0 * ldl + c0, (int)ldl,
+                                           out, (int)ldo, info);
+    GPRB_CUDA(cudaFreeAsync(info, st));
+    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotrs (inverse rows) status %d", (int)cs); return GPRB_ERR_CUDA; }
+    return GPRB_OK;
 }
 
 extern "C" int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const double *alpha, const double *Kinv,

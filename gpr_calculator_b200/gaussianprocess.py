@@ -343,10 +343,12 @@ class GP():
         if not eval_gradient:
             return MLL
 
-        Kinv = torch.empty((N, N), dtype=F64, device="cuda")
-        _lib.call("gprb_chol_inverse", ptr(K), N, N, ptr(Kinv), N, st)
         out = (ctypes_double * 2)()
         sharded = gdist.world()[1] > 1
+        if sharded and os.environ.get("GPRB_FULL_INVERSE", "0") in ("", "0"):
+            return self._lml_gradient_sharded(K, alpha, dK, r_ranges, N, NE, ya, MLL, noise_e, noise_f, is_rbf, params)
+        Kinv = torch.empty((N, N), dtype=F64, device="cuda")
+        _lib.call("gprb_chol_inverse", ptr(K), N, N, ptr(Kinv), N, st)
         # 1/2 tr(W dK/dl) over the rows of dK held by this rank (W, dK symmetric: columns j >= i,
         # off-diagonal terms doubled -- the blocks left of the diagonal are not built when sharded)
         # + 1/2 sum_i W_ii noise_i^2 (for the sigma term)
@@ -378,6 +380,51 @@ class GP():
         if sharded:
             g_l, half_w_noise, half_w_base, g_s0 = gdist.all_reduce_sum([g_l, half_w_noise, half_w_base, g_s0], device="cuda")
         # 1/2 tr(W (2/sigma) K0), K0 = K - noise:  tr(W K) = y.alpha - N
+        g_sigma = ((ya - N) - 2.0 * half_w_noise) / kernel.sigma
+        llg = np.array([g_sigma, g_l if is_rbf else g_s0, half_w_base])
+        if self.noise_bounds is None:
+            llg = llg[:-1]
+        return MLL, llg
+
+    def _lml_gradient_sharded(self, L, alpha, dK, r_ranges, N, NE, ya, MLL, noise_e, noise_f, is_rbf, params):
+        """Gradient of the LML when the rows of dK/dl are sharded (gaussianprocess.py:188-198 with the explicit
+        inverse of :195 replaced): a rank holds dK for its energy rows (K_ee part) and its force rows (K_fe and the
+        J >= I blocks of K_ff), so it needs the inverse only on Kinv[0:NE, :] and Kinv[rows, first row:].  Both are
+        solves with the factor every rank already has -- the second one with its TRAILING block only
+        (gprb_chol_inverse_rows) -- instead of potri's full 2 N^3 / 3 on every rank; the scalars are all-reduced."""
+        st = stream()
+        out = (ctypes_double * 2)()
+        kernel = self.kernel
+        Einv = None
+        if NE:
+            Einv = torch.empty((NE, N), dtype=F64, device="cuda")
+            _lib.call("gprb_chol_inverse_rows", ptr(L), N, N, 0, NE, 0, ptr(Einv), N, st)
+        g_l = half_w_noise = half_w_base = g_s0 = 0.0
+        off = 0
+        for (r0, r1) in r_ranges:
+            if r1 > r0:
+                if r1 <= NE:
+                    rows, ldr, c0 = Einv[r0:r1], N, 0                 # energy rows: a slice of Kinv[0:NE, :]
+                else:
+                    c0 = r0
+                    rows = torch.empty((r1 - r0, N - c0), dtype=F64, device="cuda")
+                    ldr = N - c0
+                    _lib.call("gprb_chol_inverse_rows", ptr(L), N, N, r0, r1, c0, ptr(rows), ldr, st)
+                dptr = c_vp(dK.data_ptr() + off * dK.stride(0) * 8) if is_rbf else c_vp(0)
+                _lib.call("gprb_lml_grad_trace_rows", N, r0, r1, ptr(alpha), ptr(rows), ldr, c0, ptr(Einv), N, dptr, N, NE,
+                          float(noise_e) ** 2, float(noise_f) ** 2, out, st)
+                g_l += out[0]
+                half_w_noise += out[1]
+                _lib.call("gprb_lml_grad_trace_rows", N, r0, r1, ptr(alpha), ptr(rows), ldr, c0, ptr(Einv), N, c_vp(0), N, NE,
+                          2.0 * float(noise_e), 2.0 * float(noise_f), out, st)
+                half_w_base += out[1]
+                if not is_rbf and r1 <= NE:
+                    # Dot: dK/dsigma0 = 0.8 * 2 sigma^2 sigma0 on the E-E block only (dot_kernel.py:58)
+                    _lib.call("gprb_w_block_sum", N, r0, r1, 0, NE, ptr(alpha), ptr(Einv), N, out, st)
+                    g_s0 = out[0] * (0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0)
+                del rows
+            off += r1 - r0
+        g_l, half_w_noise, half_w_base, g_s0 = gdist.all_reduce_sum([g_l, half_w_noise, half_w_base, g_s0], device="cuda")
         g_sigma = ((ya - N) - 2.0 * half_w_noise) / kernel.sigma
         llg = np.array([g_sigma, g_l if is_rbf else g_s0, half_w_base])
         if self.noise_bounds is None:

@@ -165,6 +165,21 @@ int gprb_lml_terms(const double *L_dev, long long ldl, int N, const double *y_de
 int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha_dev, const double *Kinv_dev, long long ldi,
                         const double *dK_rows_dev, long long lddk, int NE, double we, double wf,
                         int upper_only, double *out_host, void *stream);
+/* Rows of the inverse without forming it (row-sharded likelihood gradient: a rank that holds the rows
+ * [r0, r1) of dK with valid entries right of the diagonal only needs Kinv[r0:r1, c0:N] with c0 <= r0):
+ *   out[k*ldo + t] = Kinv[r0 + k, c0 + t],  k < r1 - r0,  t < N - c0,
+ * from the TRAILING block of the factor, K^-1[T,T] = (L_TT L_TT^T)^-1 for T = [c0, N) (cuSOLVER potrs with
+ * r1 - r0 unit right-hand sides on the (N - c0)-dimensional trailing system: 2 (N-c0)^2 (r1-r0) flops
+ * instead of the 2 N^3 / 3 of potri on every rank).  c0 = 0 gives full rows (the energy rows). */
+int gprb_chol_inverse_rows(const double *L_dev, long long ldl, int N, int r0, int r1, int c0,
+                           double *out_dev, long long ldo, void *stream);
+/* gprb_lml_grad_trace(upper_only = 2) on such slabs: Kinv_rows_dev = the slab of rows [r0, r1) from
+ * gprb_chol_inverse_rows(..., c0, ...) with leading dimension ldr; KinvE_dev = Kinv[0:NE, :] ([NE, ldE]
+ * row-major, from gprb_chol_inverse_rows(0, NE, 0)) supplies the columns j < NE of force rows
+ * (may be NULL when r1 <= NE or NE == 0). */
+int gprb_lml_grad_trace_rows(int N, int r0, int r1, const double *alpha_dev, const double *Kinv_rows_dev, long long ldr,
+                             int c0, const double *KinvE_dev, long long ldE, const double *dK_rows_dev, long long lddk,
+                             int NE, double we, double wf, double *out_host, void *stream);
 /* Live FP64 tensor-pipe roofline denominator: DMMA.8x8x4 issue-rate micro-benchmark (all SMs,
  * 16 independent accumulators per warp).  MEASURED_PEAKS.json carries no fp64 entry. */
 int gprb_fp64_dmma_peak(double *tflops_host, void *stream);

@@ -43,13 +43,14 @@ def main():
     scale = float(K1.abs().max())
 
     results = {}
-    for mode in ("peer", "nccl"):
-        os.environ["GPRB_NO_PEER"] = "0" if mode == "peer" else "1"
+    for mode in ("peer", "nccl", "fullinv"):
+        os.environ["GPRB_NO_PEER"] = "1" if mode == "nccl" else "0"
+        os.environ["GPRB_FULL_INVERSE"] = "1" if mode == "fullinv" else "0"     # potri on every rank instead of inverse rows
         gp = make_gp()
         for it in range(3):            # repeated builds re-use (and re-zero) the peer-mapped matrix
             K, dK, ranges = gp._build_K(grad=True)
             K = K.clone()
-        if mode == "peer":
+        if mode != "nccl":
             assert gp._peer is not None, "peer mapping failed: the fused gather was not exercised"
         else:
             assert getattr(gp, "_peer", None) is None
@@ -76,13 +77,32 @@ def main():
         results[mode] = (K, err, derr, lml, grad)
         gp.release_peer()
     Kp, Kn = results["peer"][0], results["nccl"][0]
+    # equal up to the summation order of row groups that straddle two CTAs: the throughput-adaptive row windows
+    # (GP._build_K) may cut the rows differently in the two runs
     bitwise = bool(torch.equal(Kp, Kn))
+    same = float((Kp - Kn).abs().max()) <= 1e-13 * scale
     lml_p, g_p = results["peer"][3], results["peer"][4]
     lml_n, g_n = results["nccl"][3], results["nccl"][4]
     # single-GPU LML on rank-local unsharded algebra: same GP code with world pretending 1 is not possible
     # inside a process group, so compare the two sharded paths with each other and K with the unsharded build
-    ok = (results["peer"][1] <= 1e-12 and results["nccl"][1] <= 1e-12 and results["peer"][2] <= 1e-12 and bitwise
-          and abs(lml_p - lml_n) <= 1e-9 * abs(lml_n) and np.allclose(g_p, g_n, rtol=1e-9, atol=1e-9))
+    lml_f, g_f = results["fullinv"][3], results["fullinv"][4]
+    # Dot kernel: the d/dsigma0 term of the sharded gradient against the potri route
+    from gpr_calculator_b200.kernels import Dot_mb
+    dot = {}
+    for mode in ("rows", "fullinv"):
+        os.environ["GPRB_FULL_INVERSE"] = "1" if mode == "fullinv" else "0"
+        gd_ = GP(kernel=Dot_mb(para=[2.0, 1.5], zeta=3), descriptor=des, noise_e=0.002, noise_f=0.1, log_file=None)
+        gd_.train_x = {"energy": e_pack, "force": f_pack}
+        gd_.y_train = y
+        dot[mode] = gd_.log_marginal_likelihood(np.array([2.0, 1.5]), eval_gradient=True)
+        gd_.release_peer()
+    dot_ok = (abs(dot["rows"][0] - dot["fullinv"][0]) <= 1e-9 * abs(dot["fullinv"][0])
+              and np.allclose(dot["rows"][1], dot["fullinv"][1], rtol=1e-7, atol=1e-7))
+    ok = (results["peer"][1] <= 1e-12 and results["nccl"][1] <= 1e-12 and results["peer"][2] <= 1e-12 and same
+          and abs(lml_p - lml_n) <= 1e-9 * abs(lml_n) and np.allclose(g_p, g_n, rtol=1e-9, atol=1e-9)
+          and abs(lml_p - lml_f) <= 1e-9 * abs(lml_f) and np.allclose(g_p, g_f, rtol=1e-7, atol=1e-7) and dot_ok)
+    if rank == 0:
+        print("gradient rows %s | potri %s ; Dot rows %s | potri %s" % (g_p, g_f, dot["rows"], dot["fullinv"]), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     print("[rank %d/%d] N=%d K err peer %.2e nccl %.2e dK err %.2e bitwise(peer,nccl)=%s lml %.9f / %.9f grad %s / %s"
