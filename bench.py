@@ -17,7 +17,7 @@ over the ranks, K all-gathered over NCCL and mirrored (strong scaling: the total
            actually evaluated (the symmetric build evaluates the J >= I blocks only), operands resident in HBM.
   e2e    : the same flops over the time of one GP.log_marginal_likelihood(theta, eval_gradient=True)
            call starting from HOST (pinned) packed arrays: H2D + row packing + K/dK build + cuSOLVER
-           potrf/potrs/potri + gradient trace + D2H of (LML, grad).
+           potrf/potrs + inverse rows (trailing-block potrs) + gradient trace + D2H of the reduced scalars.
   roofline: K_ff kernel alone (CUDA events around gprb_kff on its stream) against the FP64 tensor (DMMA)
            peak measured live by gprb_fp64_dmma_peak (MEASURED_PEAKS.json carries no fp64 entry).
   cpu_baseline: the UNMODIFIED reference C++ (oracle/_ref) on a bounded sample of the same workload,
@@ -354,9 +354,12 @@ def main():
         for n, a, b, h in prof:
             parts[n] = parts.get(n, 0.0) + a.elapsed_time(b) / args.steps
             host_parts[n] = host_parts.get(n, 0.0) + h * 1e3 / args.steps
+        # device -> host reads of a step: 2 doubles per scalar-reducing call, the potrf status word
+        scalar_calls = sum(1 for n, _, _, _ in prof if n.startswith(("gprb_lml_", "gprb_w_block_sum")))
+        d2h = (16 * scalar_calls + 4 * sum(1 for n, _, _, _ in prof if n == "gprb_chol_factor")) / args.steps
         lml, grad = res
         result["e2e"] = {"value": flops / dt * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
-                         "d2h_bytes_per_step": 16 * 5, "ms_per_step": dt * 1e3,
+                         "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
                          "call": "GP.log_marginal_likelihood(theta, eval_gradient=True) from pinned host packed arrays",
                          "device_ms_by_entry_point": {k: round(v, 3) for k, v in sorted(parts.items())},
                          "host_ms_inside_entry_point": {k: round(v, 3) for k, v in sorted(host_parts.items())},

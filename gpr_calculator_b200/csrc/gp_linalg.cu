@@ -362,12 +362,17 @@ extern "C" int gprb_chol_inverse_rows(const double *L, long long ldl, int N, int
     unit_columns_kernel<<<(nrhs + 255) / 256, 256, 0, st>>>(out, ldo, nrhs, r0 - c0);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
-    int *info = nullptr;
-    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
-    cusolverStatus_t cs = cusolverDnDpotrs(g_solver, CUBLAS_FILL_MODE_UPPER, n, nrhs, L + (long long)c0 * ldl + c0, (int)ldl,
-                                           out, (int)ldo, info);
-    GPRB_CUDA(cudaFreeAsync(info, st));
-    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotrs (inverse rows) status %d", (int)cs); return GPRB_ERR_CUDA; }
+    // what potrs does, through the 64-bit cuBLAS interface (N^2 may exceed 2^31, e.g. the S4 configuration):
+    // column-major view, K_T = U^T U with U in the upper triangle of the factor's buffer;  U^T Y = E, then U X = Y
+    const double one = 1.0;
+    const double *U = L + (long long)c0 * ldl + c0;
+    cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+                                       (int64_t)n, (int64_t)nrhs, &one, U, (int64_t)ldl, out, (int64_t)ldo);
+    cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+                                       (int64_t)n, (int64_t)nrhs, &one, U, (int64_t)ldl, out, (int64_t)ldo);
+    if (b1 != CUBLAS_STATUS_SUCCESS || b2 != CUBLAS_STATUS_SUCCESS) {
+        gprb_set_error("cublasDtrsm_64 (inverse rows) status %d / %d", (int)b1, (int)b2); return GPRB_ERR_CUDA;
+    }
     return GPRB_OK;
 }
 

@@ -345,8 +345,9 @@ class GP():
 
         out = (ctypes_double * 2)()
         sharded = gdist.world()[1] > 1
-        if sharded and os.environ.get("GPRB_FULL_INVERSE", "0") in ("", "0"):
-            return self._lml_gradient_sharded(K, alpha, dK, r_ranges, N, NE, ya, MLL, noise_e, noise_f, is_rbf, params)
+        if os.environ.get("GPRB_FULL_INVERSE", "0") in ("", "0"):
+            return self._lml_gradient_rows(K, alpha, dK, r_ranges, N, NE, ya, MLL, noise_e, noise_f, is_rbf)
+        # reference route (gaussianprocess.py:195): the explicit inverse on every rank (cuSOLVER potri)
         Kinv = torch.empty((N, N), dtype=F64, device="cuda")
         _lib.call("gprb_chol_inverse", ptr(K), N, N, ptr(Kinv), N, st)
         # 1/2 tr(W dK/dl) over the rows of dK held by this rank (W, dK symmetric: columns j >= i,
@@ -386,12 +387,17 @@ class GP():
             llg = llg[:-1]
         return MLL, llg
 
-    def _lml_gradient_sharded(self, L, alpha, dK, r_ranges, N, NE, ya, MLL, noise_e, noise_f, is_rbf, params):
-        """Gradient of the LML when the rows of dK/dl are sharded (gaussianprocess.py:188-198 with the explicit
-        inverse of :195 replaced): a rank holds dK for its energy rows (K_ee part) and its force rows (K_fe and the
-        J >= I blocks of K_ff), so it needs the inverse only on Kinv[0:NE, :] and Kinv[rows, first row:].  Both are
-        solves with the factor every rank already has -- the second one with its TRAILING block only
-        (gprb_chol_inverse_rows) -- instead of potri's full 2 N^3 / 3 on every rank; the scalars are all-reduced."""
+    def _lml_gradient_rows(self, L, alpha, dK, r_ranges, N, NE, ya, MLL, noise_e, noise_f, is_rbf):
+        """Gradient of the LML (gaussianprocess.py:188-198) without the explicit inverse of :195.
+
+        W = alpha alpha^T - K^-1 and dK/dl are symmetric, so tr(W dK) needs K^-1 only on and right of the
+        diagonal, for the rows of dK this rank holds (all rows on one GPU; its energy rows with their K_ee part and
+        its force rows with K_fe and the J >= I blocks of K_ff when row-sharded).  For a block of rows [r0, r1) that
+        is K^-1[r0:r1, r0:N], a solve with the TRAILING block of the factor only (K^-1[T,T] = (L_TT L_TT^T)^-1,
+        gprb_chol_inverse_rows), plus K^-1[0:NE, :] for the energy columns.  Walking the rows in blocks costs the
+        same 2 N^3 / 3 flops as potri but as large triangular solves (about twice potri's rate on B200), needs
+        no N x N inverse buffer, and on G GPUs every rank solves only for its own rows (about 1/G of the work,
+        no communication); the resulting scalars are all-reduced."""
         st = stream()
         out = (ctypes_double * 2)()
         kernel = self.kernel
@@ -399,32 +405,46 @@ class GP():
         if NE:
             Einv = torch.empty((NE, N), dtype=F64, device="cuda")
             _lib.call("gprb_chol_inverse_rows", ptr(L), N, N, 0, NE, 0, ptr(Einv), N, st)
-        g_l = half_w_noise = half_w_base = g_s0 = 0.0
+        blk = max(512, -(-N // 16))
+        pieces = []                       # (r0, r1, row offset into dK)
         off = 0
         for (r0, r1) in r_ranges:
-            if r1 > r0:
-                if r1 <= NE:
-                    rows, ldr, c0 = Einv[r0:r1], N, 0                 # energy rows: a slice of Kinv[0:NE, :]
-                else:
-                    c0 = r0
-                    rows = torch.empty((r1 - r0, N - c0), dtype=F64, device="cuda")
-                    ldr = N - c0
-                    _lib.call("gprb_chol_inverse_rows", ptr(L), N, N, r0, r1, c0, ptr(rows), ldr, st)
-                dptr = c_vp(dK.data_ptr() + off * dK.stride(0) * 8) if is_rbf else c_vp(0)
-                _lib.call("gprb_lml_grad_trace_rows", N, r0, r1, ptr(alpha), ptr(rows), ldr, c0, ptr(Einv), N, dptr, N, NE,
-                          float(noise_e) ** 2, float(noise_f) ** 2, out, st)
-                g_l += out[0]
-                half_w_noise += out[1]
-                _lib.call("gprb_lml_grad_trace_rows", N, r0, r1, ptr(alpha), ptr(rows), ldr, c0, ptr(Einv), N, c_vp(0), N, NE,
-                          2.0 * float(noise_e), 2.0 * float(noise_f), out, st)
-                half_w_base += out[1]
-                if not is_rbf and r1 <= NE:
-                    # Dot: dK/dsigma0 = 0.8 * 2 sigma^2 sigma0 on the E-E block only (dot_kernel.py:58)
-                    _lib.call("gprb_w_block_sum", N, r0, r1, 0, NE, ptr(alpha), ptr(Einv), N, out, st)
-                    g_s0 = out[0] * (0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0)
-                del rows
+            cuts = [r0] + ([NE] if r0 < NE < r1 else [])
+            a = cuts[-1]
+            while a < r1 and a >= NE:     # force rows: blocks of about N/16 rows
+                a = min(a + blk, r1)
+                cuts.append(a)
+            if cuts[-1] != r1:
+                cuts.append(r1)
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                if b > a:
+                    pieces.append((a, b, off + (a - r0)))
             off += r1 - r0
-        g_l, half_w_noise, half_w_base, g_s0 = gdist.all_reduce_sum([g_l, half_w_noise, half_w_base, g_s0], device="cuda")
+        g_l = half_w_noise = half_w_base = g_s0 = 0.0
+        for (r0, r1, doff) in pieces:
+            if r1 <= NE:
+                rows, ldr, c0 = Einv[r0:r1], N, 0                 # energy rows: a slice of K^-1[0:NE, :]
+            else:
+                c0 = r0
+                rows = torch.empty((r1 - r0, N - c0), dtype=F64, device="cuda")
+                ldr = N - c0
+                _lib.call("gprb_chol_inverse_rows", ptr(L), N, N, r0, r1, c0, ptr(rows), ldr, st)
+            dptr = c_vp(dK.data_ptr() + doff * dK.stride(0) * 8) if is_rbf else c_vp(0)
+            ldd = dK.stride(0) if is_rbf else N
+            _lib.call("gprb_lml_grad_trace_rows", N, r0, r1, ptr(alpha), ptr(rows), ldr, c0, ptr(Einv), N, dptr, ldd, NE,
+                      float(noise_e) ** 2, float(noise_f) ** 2, out, st)
+            g_l += out[0]
+            half_w_noise += out[1]
+            _lib.call("gprb_lml_grad_trace_rows", N, r0, r1, ptr(alpha), ptr(rows), ldr, c0, ptr(Einv), N, c_vp(0), N, NE,
+                      2.0 * float(noise_e), 2.0 * float(noise_f), out, st)
+            half_w_base += out[1]
+            if not is_rbf and r1 <= NE:
+                # Dot: dK/dsigma0 = 0.8 * 2 sigma^2 sigma0 on the E-E block only (dot_kernel.py:58)
+                _lib.call("gprb_w_block_sum", N, r0, r1, 0, NE, ptr(alpha), ptr(Einv), N, out, st)
+                g_s0 += out[0] * (0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0)
+            del rows
+        if gdist.world()[1] > 1:
+            g_l, half_w_noise, half_w_base, g_s0 = gdist.all_reduce_sum([g_l, half_w_noise, half_w_base, g_s0], device="cuda")
         g_sigma = ((ya - N) - 2.0 * half_w_noise) / kernel.sigma
         llg = np.array([g_sigma, g_l if is_rbf else g_s0, half_w_base])
         if self.noise_bounds is None:

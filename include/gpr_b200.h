@@ -168,7 +168,7 @@ int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha_dev, const do
 /* Rows of the inverse without forming it (row-sharded likelihood gradient: a rank that holds the rows
  * [r0, r1) of dK with valid entries right of the diagonal only needs Kinv[r0:r1, c0:N] with c0 <= r0):
  *   out[k*ldo + t] = Kinv[r0 + k, c0 + t],  k < r1 - r0,  t < N - c0,
- * from the TRAILING block of the factor, K^-1[T,T] = (L_TT L_TT^T)^-1 for T = [c0, N) (cuSOLVER potrs with
+ * from the TRAILING block of the factor, K^-1[T,T] = (L_TT L_TT^T)^-1 for T = [c0, N) (two cuBLAS trsm, i.e. potrs, with
  * r1 - r0 unit right-hand sides on the (N - c0)-dimensional trailing system: 2 (N-c0)^2 (r1-r0) flops
  * instead of the 2 N^3 / 3 of potri on every rank).  c0 = 0 gives full rows (the energy rows). */
 int gprb_chol_inverse_rows(const double *L_dev, long long ldl, int N, int r0, int r1, int c0,
