@@ -49,8 +49,8 @@ WORKLOADS = {
 }
 
 
-# DRAM bytes per launch of the K_ff(+grad) kernel, from ncu (13.28 GB read + 17.25 GB written at S5)
-KFF_DRAM_TRAFFIC = {"s5": 30.54e9}
+# DRAM bytes per launch of the K_ff(+grad) kernel, from ncu (13.82 GB read + 17.18 GB written at S5)
+KFF_DRAM_TRAFFIC = {"s5": 30.995e9}
 
 
 def flops_of(p_ff, p_ef, p_ee, d=D):
