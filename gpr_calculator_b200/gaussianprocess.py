@@ -50,6 +50,28 @@ def _zero_build_targets(K, NE, chunks=16):
         K[r:r + per, r:].zero_()
 
 
+def _row_pieces(r_ranges, NE, N, parts=16, min_rows=512):
+    """Blocks of rows for the inverse-rows likelihood gradient: the row ranges a rank holds (their rows of dK
+    stored one range after the other) cut at the energy / force boundary and, for force rows, into blocks of
+    about N / parts rows (>= min_rows).  Returns [(r0, r1, first row of the block inside dK)]."""
+    blk = max(min_rows, -(-N // parts))
+    pieces = []
+    off = 0
+    for (r0, r1) in r_ranges:
+        cuts = [r0] + ([NE] if r0 < NE < r1 else [])
+        a = cuts[-1]
+        while a < r1 and a >= NE:     # force rows
+            a = min(a + blk, r1)
+            cuts.append(a)
+        if cuts[-1] != r1:
+            cuts.append(r1)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b > a:
+                pieces.append((a, b, off + (a - r0)))
+        off += r1 - r0
+    return pieces
+
+
 def _lazy_SO3():
     from .SO3 import SO3
     return SO3
@@ -405,23 +427,8 @@ class GP():
         if NE:
             Einv = torch.empty((NE, N), dtype=F64, device="cuda")
             _lib.call("gprb_chol_inverse_rows", ptr(L), N, N, 0, NE, 0, ptr(Einv), N, st)
-        blk = max(512, -(-N // 16))
-        pieces = []                       # (r0, r1, row offset into dK)
-        off = 0
-        for (r0, r1) in r_ranges:
-            cuts = [r0] + ([NE] if r0 < NE < r1 else [])
-            a = cuts[-1]
-            while a < r1 and a >= NE:     # force rows: blocks of about N/16 rows
-                a = min(a + blk, r1)
-                cuts.append(a)
-            if cuts[-1] != r1:
-                cuts.append(r1)
-            for a, b in zip(cuts[:-1], cuts[1:]):
-                if b > a:
-                    pieces.append((a, b, off + (a - r0)))
-            off += r1 - r0
         g_l = half_w_noise = half_w_base = g_s0 = 0.0
-        for (r0, r1, doff) in pieces:
+        for (r0, r1, doff) in _row_pieces(r_ranges, NE, N):
             if r1 <= NE:
                 rows, ldr, c0 = Einv[r0:r1], N, 0                 # energy rows: a slice of K^-1[0:NE, :]
             else:

@@ -211,6 +211,44 @@ def test_inverse_large_n_route_matches_potri(monkeypatch):
         assert rel_err(o, ref) <= 1e-10 and np.abs(o - o.T).max() == 0.0
 
 
+def test_inverse_rows_and_gradient_routes(g, monkeypatch):
+    """gprb_chol_inverse_rows against numpy (trailing-block solves), and the likelihood gradient through the blocked
+    inverse-rows route against the literal route of the reference (explicit inverse, gaussianprocess.py:195)."""
+    import torch
+    from gpr_calculator_b200 import _lib
+    from gpr_calculator_b200.device import ptr, stream
+    rng = np.random.default_rng(4)
+    N = 257
+    A = rng.normal(size=(N, N))
+    K = A @ A.T + N * np.eye(N)
+    ref = np.linalg.inv(K)
+    Kd = torch.as_tensor(K, device="cuda").contiguous()
+    _lib.call("gprb_chol_factor", ptr(Kd), N, N, stream())
+    for (r0, r1, c0) in ((0, 17, 0), (40, 97, 40), (40, 97, 11), (200, 257, 200), (256, 257, 256), (5, 5, 5)):
+        out = torch.full((max(r1 - r0, 1), N - c0 + 3), 7.0, dtype=torch.float64, device="cuda")     # padded leading dimension
+        _lib.call("gprb_chol_inverse_rows", ptr(Kd), N, N, r0, r1, c0, ptr(out), N - c0 + 3, stream())
+        if r1 > r0:
+            assert rel_err(out[:, :N - c0].cpu().numpy(), ref[r0:r1, c0:]) <= 1e-10
+            assert bool((out[:, N - c0:] == 7.0).all())
+    for kernel, theta in (("RBF", np.array([1.3, 0.25])), ("Dot", np.array([2.0, 1.5]))):
+        gp = _model(g, kernel)
+        monkeypatch.setenv("GPRB_FULL_INVERSE", "0")
+        lml_r, grad_r = gp.log_marginal_likelihood(theta, eval_gradient=True)
+        monkeypatch.setenv("GPRB_FULL_INVERSE", "1")
+        lml_f, grad_f = gp.log_marginal_likelihood(theta, eval_gradient=True)
+        assert lml_r == lml_f
+        assert np.allclose(grad_r, grad_f, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(grad_f).max()))
+    # a noise hyper-parameter adds the third gradient component (noise_bounds, gaussianprocess.py:196-198)
+    gp = _model(g, "RBF")
+    gp.noise_bounds = [1e-4, 1e-1]
+    th = np.array([1.3, 0.25, 0.004])
+    monkeypatch.setenv("GPRB_FULL_INVERSE", "0")
+    _, grad_r = gp.log_marginal_likelihood(th, eval_gradient=True)
+    monkeypatch.setenv("GPRB_FULL_INVERSE", "1")
+    _, grad_f = gp.log_marginal_likelihood(th, eval_gradient=True)
+    assert len(grad_r) == 3 and np.allclose(grad_r, grad_f, rtol=1e-9, atol=1e-9 * np.abs(grad_f).max())
+
+
 def test_sparsify_removes_duplicated_points(g):
     """CUR sparsification on device (gaussianprocess.py:1004-1023, 1165-1182): an exactly duplicated training
     structure puts K's smallest eigenvalues below the tolerance and its rows are dropped."""

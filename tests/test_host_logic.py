@@ -203,3 +203,47 @@ def test_synthetic_pair_counts_and_windows():
     w = gd.row_windows([32] * 7, [28] * 40, 4, upper=True)
     sizes = [f1 - f0 for _, (f0, f1) in w]
     assert sum(sizes) == 40 and sizes[0] < sizes[-1]      # early rows carry longer sweeps
+
+
+def test_row_pieces_cover_rows_once():
+    """Blocks of the inverse-rows likelihood gradient: every held row exactly once, never across the energy / force
+    boundary, dK offsets consecutive."""
+    from gpr_calculator_b200.gaussianprocess import _row_pieces
+    for NE, N, ranges in ((340, 32980, [(0, 32980)]), (0, 900, [(0, 900)]), (5, 5, [(0, 5)]), (7, 100, [(2, 5), (40, 73)]),
+                          (7, 100, [(0, 7), (7, 100)]), (340, 32980, [(170, 340), (20000, 32980)]), (3, 50, [(0, 0), (3, 3)])):
+        pieces = _row_pieces(ranges, NE, N, parts=16, min_rows=4)
+        rows, off = [], 0
+        for (a, b, doff) in pieces:
+            assert b > a and (b <= NE or a >= NE)
+            assert doff == off
+            off += b - a
+            rows += list(range(a, b))
+        want = [i for (r0, r1) in ranges for i in range(r0, r1)]
+        assert rows == want
+
+
+def test_trailing_block_inverse_identity():
+    """K^-1[T, T] = (L_TT L_TT^T)^-1 for a trailing index set T (what gprb_chol_inverse_rows relies on)."""
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(40, 40))
+    K = A @ A.T + 40 * np.eye(40)
+    L = np.linalg.cholesky(K)
+    Kinv = np.linalg.inv(K)
+    for c0 in (0, 7, 33):
+        LT = L[c0:, c0:]
+        assert np.allclose(np.linalg.inv(LT @ LT.T), Kinv[c0:, c0:], rtol=1e-10, atol=1e-12)
+
+
+def test_zero_build_targets_and_slab_pointers():
+    import torch
+    from gpr_calculator_b200.gaussianprocess import _zero_build_targets
+    from gpr_calculator_b200.dist import slab_pointers
+    NE, NF = 3, 11
+    N = NE + 3 * NF
+    K = torch.ones((N, N), dtype=torch.float64)
+    _zero_build_targets(K, NE, chunks=4)
+    i, j = np.indices((N, N))
+    must_zero = (i >= NE) & ((j < NE) | (j >= i))           # K_fe columns and the F-F part on / right of the diagonal
+    assert bool((K.numpy()[must_zero] == 0).all())
+    assert bool((K.numpy()[:NE] == 1).all())                # energy rows untouched
+    assert slab_pointers([1000, 5000], 4, 2, 10) == [1000 + (4 * 10 + 2) * 8, 5000 + (4 * 10 + 2) * 8]
