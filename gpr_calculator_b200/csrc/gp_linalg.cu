@@ -422,6 +422,47 @@ extern "C" int gprb_predict(int m, int N, const double *Ks, long long ldks, cons
     return GPRB_OK;
 }
 
+// one CTA per test row: mean = Ks[i,:].alpha ; var = max(diag - |Y[i,:]|^2, 0) with Y = (L^-1 Ks^T)^T
+__global__ void __launch_bounds__(256) predict_rows_chol_kernel(int N, const double *__restrict__ Ks, long long ldks,
+                                                                const double *__restrict__ alpha, const double *__restrict__ Y,
+                                                                const double *__restrict__ diag, double *mean, double *var) {
+    __shared__ double sh[32];
+    const int i = blockIdx.x;
+    const double *k = Ks + (long long)i * ldks;
+    const double *y = Y + (long long)i * N;
+    double m = 0.0, v = 0.0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) { m = fma(k[j], alpha[j], m); const double t = y[j]; v = fma(t, t, v); }
+    m = block_sum(m, sh);
+    v = block_sum(v, sh);
+    if (threadIdx.x == 0) {
+        mean[i] = m;
+        const double r = diag[i] - v;
+        var[i] = r < 0.0 ? 0.0 : r;
+    }
+}
+
+extern "C" int gprb_predict_chol(int m, int N, const double *Ks, long long ldks, const double *alpha,
+                                 const double *L, long long ldl, const double *diag,
+                                 double *mean, double *var, double *work, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(Ks && alpha && mean && var && L && diag && work && m >= 0 && N > 0, "gprb_predict_chol: bad argument");
+    if (m == 0) return GPRB_OK;
+    int rc = handles(st);
+    if (rc) return rc;
+    // k*^T K^-1 k* = |L^-1 k*|^2: one triangular solve with m right-hand sides (m N^2 flops) instead of the
+    // product with the explicit inverse (2 m N^2).  Column-major view: work (N x m) = Ks^T, U^T Y = Ks^T.
+    GPRB_CUDA(cudaMemcpy2DAsync(work, (size_t)N * sizeof(double), Ks, (size_t)ldks * sizeof(double), (size_t)N * sizeof(double), m,
+                                cudaMemcpyDeviceToDevice, st));
+    const double one = 1.0;
+    cublasStatus_t bs = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+                                       (int64_t)N, (int64_t)m, &one, L, (int64_t)ldl, work, (int64_t)N);
+    if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDtrsm_64 (predict) status %d", (int)bs); return GPRB_ERR_CUDA; }
+    predict_rows_chol_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, work, diag, mean, var);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
 // dst[j][i] = src[i][j] for a rows x cols block (32 x 32 tiles through shared memory)
 __global__ void transpose_copy_kernel(double *dst, long long ldd, const double *src, long long lds, int rows, int cols) {
     __shared__ double t[32][33];

@@ -169,6 +169,10 @@ class GP():
 
     @property
     def _K_inv(self):
+        # materialised on first use: fit() no longer forms the inverse eagerly (gaussianprocess.py:317) because
+        # batched predictions go through the factor (_mean_var)
+        if self._Kinv_dev is None and self._L_dev is not None:
+            self.set_K_inv()
         return None if self._Kinv_dev is None else self._Kinv_dev.cpu().numpy()
 
     @_K_inv.setter
@@ -526,7 +530,8 @@ class GP():
         self.N_forces_queue = 0
         self.N_queue = 0
         self.fits += 1
-        self.set_K_inv()
+        # set_K_inv() of gaussianprocess.py:317 is deferred to the first consumer of the explicit inverse
+        # (single-structure variance, return_cov, the _K_inv attribute): see _mean_var
 
     def _predict_device(self, X, train_x, f_tol, return_std):
         """K* on device, mean and variance (gaussianprocess.py:338, 368-377 / 880, 904-908)."""
@@ -537,17 +542,37 @@ class GP():
         if f is not None:
             Xp["force"] = f
         K_trans, _ = self.kernel.k_total_device(Xp, train_x, f_tol=f_tol, grad=False)
-        m, N = K_trans.shape
-        mean = torch.empty(m, dtype=F64, device="cuda")
-        var = diag = work = None
+        diag = None
         if return_std:
             diag = self.kernel.diag_device(X if isinstance(self.kernel, Dot_mb) else Xp, _packed_ok=True)
-            var = torch.empty(m, dtype=F64, device="cuda")
-            work = torch.empty((m, N), dtype=F64, device="cuda")
-            self.set_K_inv()
-        _lib.call("gprb_predict", m, N, ptr(K_trans), N, ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
-                  ptr(diag), ptr(mean), ptr(var), ptr(work), stream())
+        mean, var = self._mean_var(K_trans, diag)
         return K_trans, mean, var
+
+    # rows of K* from which the variance goes through the Cholesky factor (one trsm, m N^2 flops) instead of
+    # the explicit inverse (gemm, 2 m N^2 flops, gaussianprocess.py:369,905): a triangular solve with few
+    # right-hand sides is latency bound (S5: m = 97: 15 ms vs 8 ms; m = 582: 31 vs 37 ms; m = 3104: 113 vs 190 ms,
+    # tools/predict_routes.py), so single structures keep the reference's route
+    CHOL_VARIANCE_MIN_ROWS = 512
+
+    def _mean_var(self, K_trans, diag):
+        """mean = K* alpha and, when `diag` (the prior variances) is given, var = max(diag - k*^T K^-1 k*, 0)."""
+        m, N = K_trans.shape
+        mean = torch.empty(m, dtype=F64, device="cuda")
+        if diag is None:
+            _lib.call("gprb_predict", m, N, ptr(K_trans), N, ptr(self._alpha_dev), c_vp(0), N, c_vp(0), ptr(mean), c_vp(0),
+                      c_vp(0), stream())
+            return mean, None
+        var = torch.empty(m, dtype=F64, device="cuda")
+        work = torch.empty((m, N), dtype=F64, device="cuda")
+        route = os.environ.get("GPRB_VARIANCE_ROUTE", "auto")          # auto | chol | inverse
+        if self._L_dev is not None and (route == "chol" or (route == "auto" and m >= self.CHOL_VARIANCE_MIN_ROWS)):
+            _lib.call("gprb_predict_chol", m, N, ptr(K_trans), N, ptr(self._alpha_dev), ptr(self._L_dev), N,
+                      ptr(diag), ptr(mean), ptr(var), ptr(work), stream())
+        else:
+            self.set_K_inv()
+            _lib.call("gprb_predict", m, N, ptr(K_trans), N, ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
+                      ptr(diag), ptr(mean), ptr(var), ptr(work), stream())
+        return mean, var
 
     def predict(self, X, stress=False, total_E=False, return_std=False, return_cov=False):
         """
@@ -903,17 +928,11 @@ class GP():
         e1, (f1, sa, sb) = energy_pack(E_t), stress_packs(F_t)
         train_x = self.get_train_x()
         K, K1 = self.kernel.k_total_stress_device({"energy": e1, "force": (f1, sa, sb)}, train_x, tol=f_tol)
-        m, N = K.shape
-        mean = torch.empty(m, dtype=F64, device="cuda")
-        var = diag = work = None
+        diag = None
         if return_std:
             diag = self.kernel.diag_device({"energy": E_t, "force": (F_t[0], F_t[1][:, :, :3].contiguous(), F_t[2], F_t[3])}
                                            if isinstance(self.kernel, Dot_mb) else {"energy": e1, "force": f1}, _packed_ok=True)
-            var = torch.empty(m, dtype=F64, device="cuda")
-            work = torch.empty((m, N), dtype=F64, device="cuda")
-            self.set_K_inv()
-        _lib.call("gprb_predict", m, N, ptr(K), N, ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
-                  ptr(diag), ptr(mean), ptr(var), ptr(work), stream())
+        mean, var = self._mean_var(K, diag)
         y_mean = mean.cpu().numpy()
         E = y_mean[0] * n
         F_all = y_mean[1:].reshape(n, 3)

@@ -192,6 +192,13 @@ int gprb_predict(int m, int N, const double *Ks_dev, long long ldks, const doubl
                  const double *Kinv_dev, long long ldi, const double *diag_dev,
                  double *mean_dev, double *var_dev, double *work_dev, void *stream);
 
+/* Same outputs from the Cholesky factor instead of the explicit inverse: var[i] = max(diag[i] - |L^-1 Ks[i,:]^T|^2, 0)
+ * (one cuBLAS trsm with m right-hand sides, m N^2 flops instead of 2 m N^2, no N x N inverse to form after a fit).
+ * Used for batches of test rows; work_dev: [m, N] scratch. */
+int gprb_predict_chol(int m, int N, const double *Ks_dev, long long ldks, const double *alpha_dev,
+                      const double *L_dev, long long ldl, const double *diag_dev,
+                      double *mean_dev, double *var_dev, double *work_dev, void *stream);
+
 /* ---- SO(3) power-spectrum descriptor (gpr_calc/SO3.py:186-727), batched over structures --------
  * Atoms of all structures are concatenated; atom_ptr[S+1] gives the first atom of each structure,
  * struct_of[n_atoms] the structure of each atom.  All pointers are device pointers.

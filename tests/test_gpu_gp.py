@@ -249,6 +249,49 @@ def test_inverse_rows_and_gradient_routes(g, monkeypatch):
     assert len(grad_r) == 3 and np.allclose(grad_r, grad_f, rtol=1e-9, atol=1e-9 * np.abs(grad_f).max())
 
 
+def test_variance_routes_match_numpy(g, monkeypatch):
+    """Predictive variance through the explicit inverse (gprb_predict, the reference's formula) and through the Cholesky
+    factor (gprb_predict_chol, used for batches) against numpy, and the two routes through GP.predict_structures."""
+    import torch
+    from gpr_calculator_b200 import _lib
+    from gpr_calculator_b200.device import ptr, stream
+    rng = np.random.default_rng(8)
+    N, m = 300, 41
+    A = rng.normal(size=(N, N))
+    K = A @ A.T + N * np.eye(N)
+    Ks = rng.normal(size=(m, N + 5))[:, :N]                 # rows with a leading dimension > N
+    alpha = rng.normal(size=N)
+    prior = 10.0 + rng.uniform(size=m)
+    quad = np.einsum("ij,ij->i", Ks @ np.linalg.inv(K), Ks)
+    want_var = np.maximum(prior - quad, 0.0)
+    Ld = torch.as_tensor(K, device="cuda").contiguous()
+    _lib.call("gprb_chol_factor", ptr(Ld), N, N, stream())
+    Kinv = torch.empty((N, N), dtype=torch.float64, device="cuda")
+    _lib.call("gprb_chol_inverse", ptr(Ld), N, N, ptr(Kinv), N, stream())
+    Kd = torch.as_tensor(np.ascontiguousarray(rng.normal(size=(m, N + 5))), device="cuda")
+    Kd[:, :N] = torch.as_tensor(Ks, device="cuda")
+    ad, dd = torch.as_tensor(alpha, device="cuda"), torch.as_tensor(prior, device="cuda")
+    for name in ("gprb_predict", "gprb_predict_chol"):
+        mean = torch.empty(m, dtype=torch.float64, device="cuda")
+        var = torch.empty(m, dtype=torch.float64, device="cuda")
+        work = torch.empty((m, N), dtype=torch.float64, device="cuda")
+        second = (ptr(Kinv), N) if name == "gprb_predict" else (ptr(Ld), N)
+        _lib.call(name, m, N, ptr(Kd), N + 5, ptr(ad), second[0], second[1], ptr(dd), ptr(mean), ptr(var), ptr(work), stream())
+        assert rel_err(mean.cpu().numpy(), Ks @ alpha) <= 1e-12
+        assert np.abs(var.cpu().numpy() - want_var).max() <= 1e-11 * prior.max()
+    # through the GP API: a batch forced through either route gives the same E / F / sigma
+    gp = _model(g)
+    strucs = [_atoms(g, g["t%d_pos" % k]) for k in range(3)]
+    out = {}
+    for route in ("inverse", "chol"):
+        monkeypatch.setenv("GPRB_VARIANCE_ROUTE", route)
+        out[route] = gp.predict_structures(strucs, return_std=True, f_tol=1e-10, batch=3)
+    bound = std_tolerance(g["K_b"], 0.002, 0.1, 3, np.array([4.0]))       # on the variance (test_oracle_golden.py)
+    for a, b in zip(out["inverse"], out["chol"]):
+        assert abs(a[0] - b[0]) <= 1e-10 and np.abs(a[1] - b[1]).max() <= 1e-10
+        assert np.abs(np.concatenate(([a[3]], a[4].ravel())) ** 2 - np.concatenate(([b[3]], b[4].ravel())) ** 2).max() <= bound
+
+
 def test_sparsify_removes_duplicated_points(g):
     """CUR sparsification on device (gaussianprocess.py:1004-1023, 1165-1182): an exactly duplicated training
     structure puts K's smallest eigenvalues below the tolerance and its rows are dropped."""
