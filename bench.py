@@ -53,6 +53,9 @@ WORKLOADS = {
 KFF_DRAM_TRAFFIC = {"s5": 30.995e9}
 
 
+SO3_CPU_SECONDS = []     # numpy port of SO3.calculate (oracle/so3.py), seconds per structure of the CPU sample
+
+
 def flops_of(p_ff, p_ef, p_ee, d=D):
     return 32.0 * d * p_ff + 8.0 * d * p_ef + 2.0 * d * p_ee
 
@@ -114,9 +117,12 @@ def cpu_sample(n_struct, nrep, seed0):
     from oracle import so3 as oso3
     from gpr_calculator_b200.synthetic import cu_fcc
     e_items, f_items = [], []
+    global SO3_CPU_SECONDS
     for k in range(n_struct):
         at, _, _ = cu_fcc(nrep, seed0 + k)
+        t0 = time.perf_counter()
         x, dxdr, seq = oso3.so3_calculate(at.positions, at.cell, at.pbc, at.numbers, 3, 4, 5.0, 2.0)
+        SO3_CPU_SECONDS.append(time.perf_counter() - t0)
         ele = np.asarray(at.numbers, dtype=np.int32)
         e_items.append((x, ele))
         for i in range(len(at)):
@@ -409,12 +415,32 @@ def main():
                                          "device, host Atoms in, numpy E/F/std out; every rank predicts its own share (replicas); "
                                          "single_call_ms = one GP.predict_structure(atoms, stress=False, return_std=True)"}
 
+    # ---- descriptor producer: SO3 of the whole training set on the device (host Atoms in, device x / dxdr / seq out) ----
+    atoms_list = [a for a, _, _ in labelled]
+    des.calculate_batch(atoms_list[:64], to_host=False)
+    barrier()
+    t0 = time.perf_counter()
+    n_seq = 0
+    for s0 in range(0, len(atoms_list), 64):
+        r = des.calculate_batch(atoms_list[s0:s0 + 64], to_host=False)
+        n_seq += int(r["seq"].shape[0])
+    barrier()
+    dt_so3 = time.perf_counter() - t0
+    n_atoms = sum(len(a) for a in atoms_list)
+    result["so3"] = {"value": len(atoms_list) / dt_so3, "unit": "structures/s", "atoms_per_structure": n_atoms // len(atoms_list),
+                     "seq_rows": n_seq, "output_gb_per_s": 8.0 * (n_atoms * D + n_seq * 3 * D) / dt_so3 * 1e-9,
+                     "call": "SO3.calculate_batch(64 structures, to_host=False): neighbour search, radial integrals, power spectrum "
+                             "and dx/dr on device; bound by FP64 special functions, not HBM"}
+
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = args.cpu_structures or 8
         gf, dt, kind, sample = run_cpu(n_cpu, nrep, seed0, 1, 0, threads)
         result["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample,
                                   "seconds": dt}
+        if SO3_CPU_SECONDS:
+            result["so3"]["cpu_port_structures_per_s"] = 1.0 / float(np.mean(SO3_CPU_SECONDS))
+            result["so3"]["cpu_port"] = "oracle/so3.py (numpy restatement of SO3.calculate), 1 core, same structures"
     if world > 1 and getattr(gp, "_peer", None) is None and gdist.peer_gather_enabled():
         result["config"]["gather"] = "NCCL all-gather (peer mapping unavailable)"
     if rank == 0:
