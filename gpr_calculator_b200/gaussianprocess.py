@@ -432,7 +432,7 @@ class GP():
             Einv = torch.empty((NE, N), dtype=F64, device="cuda")
             _lib.call("gprb_chol_inverse_rows", ptr(L), N, N, 0, NE, 0, ptr(Einv), N, st)
         g_l = half_w_noise = half_w_base = g_s0 = 0.0
-        for (r0, r1, doff) in _row_pieces(r_ranges, NE, N):
+        for (r0, r1, doff) in _row_pieces(r_ranges, NE, N, parts=int(os.environ.get("GPRB_INVERSE_ROW_PARTS", "16"))):
             if r1 <= NE:
                 rows, ldr, c0 = Einv[r0:r1], N, 0                 # energy rows: a slice of K^-1[0:NE, :]
             else:
