@@ -13,7 +13,7 @@
 
 void gprb_set_error(const char *fmt, ...);
 int gprb_pool_init();            // stream-ordered pool of the current device, memory kept across synchronisations (pack.cu)
-void gprb_pool_free(void *ptr);  // cudaFreeAsync on the legacy default stream (NULL is fine)
+void gprb_pool_free(void *ptr, cudaStream_t st);  // cudaFreeAsync ordered on st (NULL pointer is fine)
 
 // kernels launched by this library so far (gprb_launch_count); bumped next to every <<< >>>
 #include <atomic>
@@ -60,6 +60,7 @@ extern std::atomic<long long> g_gprb_launches;
 struct gprb_pack {
     int n_groups = 0, n_rows = 0, d = 0, ncols = 0, ncomp = 0, ks = 0, n_tiles = 0;
     int device = 0;
+    cudaStream_t stream = nullptr; // creation stream: the pack's buffers are returned to the pool in its order
     std::vector<int> group_rows;   // host, [G]
     std::vector<int> row_ptr;      // host, [G+1]  first flat row of each group
     // per-group species histogram (non-dropped rows) for pair counting

@@ -127,17 +127,20 @@ int gprb_pool_init() {
     return GPRB_OK;
 }
 
-// Frees are ordered on the legacy default stream: it synchronises with every blocking stream, so work that
-// still reads the pack on another (blocking) stream completes first.
-void gprb_pool_free(void *ptr) {
-    if (ptr) cudaFreeAsync(ptr, (cudaStream_t)0);
+// Frees are ordered on the stream the pack was created on (the stream its consumers normally run on; the header
+// requires that no call using a pack is in flight when it is destroyed).  If that stream no longer exists the
+// synchronous cudaFree is the safe fallback.
+void gprb_pool_free(void *ptr, cudaStream_t st) {
+    if (!ptr) return;
+    if (cudaFreeAsync(ptr, st) != cudaSuccess) { cudaGetLastError(); cudaFree(ptr); }
 }
 
 extern "C" void gprb_pack_destroy(gprb_pack *p) {
     if (!p) return;
-    gprb_pool_free(p->P); gprb_pool_free(p->norm); gprb_pool_free(p->elep); gprb_pool_free(p->row_group);
-    gprb_pool_free(p->tile_rec); gprb_pool_free(p->d_row_ptr); gprb_pool_free(p->d_group_rows);
-    gprb_pool_free(p->sched); gprb_pool_free(p->sched_ent);
+    cudaStream_t st = p->stream;
+    gprb_pool_free(p->P, st); gprb_pool_free(p->norm, st); gprb_pool_free(p->elep, st); gprb_pool_free(p->row_group, st);
+    gprb_pool_free(p->tile_rec, st); gprb_pool_free(p->d_row_ptr, st); gprb_pool_free(p->d_group_rows, st);
+    gprb_pool_free(p->sched, st); gprb_pool_free(p->sched_ent, st);
     delete p;
 }
 
@@ -153,6 +156,7 @@ extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_
     GPRB_REQUIRE(ncols == 0 || dxdr_any != nullptr || n_groups == 0, "gprb_pack_create: dxdr is NULL for a force pack");
     { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
     gprb_pack *p = new gprb_pack();
+    p->stream = st;
     GPRB_CUDA(cudaGetDevice(&p->device));
     p->n_groups = n_groups; p->d = d; p->ncols = ncols; p->ncomp = 1 + ncols; p->ks = (d + 3) / 4;
     p->group_rows.assign(group_rows_host, group_rows_host + n_groups);
