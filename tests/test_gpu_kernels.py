@@ -295,3 +295,73 @@ def test_kff_is_psd_and_deterministic():
     assert torch.equal(K1, K2)                              # fixed-order reductions: bitwise reproducible
     w = torch.linalg.eigvalsh(K1)
     assert w.min().item() >= -1e-9 * w.max().item()
+
+
+def test_empty_groups_and_empty_sides(oracle_libs):
+    """Groups without rows (a force centre with no neighbour inside rcut) give zero rows / columns, and
+    a side without groups gives an empty block, like the reference's loops."""
+    from gpr_calculator_b200.kernels import rbf_kernel as rk, dot_kernel as dk
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(11)
+    d = 30
+
+    def with_holes(items, holes):
+        out = list(items)
+        for h in holes:
+            proto = out[0]
+            empty = tuple(np.zeros((0,) + a.shape[1:], dtype=a.dtype) for a in proto)
+            out.insert(h, empty)
+        return out
+
+    F1 = list_to_tuple(with_holes(make_force(rng, 5, lo=3, hi=20), (0, 3, 7)))
+    F2 = list_to_tuple(with_holes(make_force(rng, 4, lo=3, hi=20), (2,)))
+    # (an energy item is a whole structure: never empty -- the reference would divide by its zero atom count)
+    E1 = list_to_tuple(make_energy(rng, 3, lo=3, hi=20), mode="energy")
+    assert F1[-1].count(0) == 3 and F2[-1].count(0) == 1
+    O, OD = oracle_libs.RBFOracle("port"), oracle_libs.DotOracle("port")
+    for grad in (False, True):
+        for fn_g, fn_o, a, b in ((rk.kff_C, O.kff_C, F1, F2), (rk.kef_C, O.kef_C, E1, F1), (rk.kee_C, O.kee_C, E1, E1)):
+            got, ref = fn_g(a, b, 1.2, 0.8, 2.0, grad=grad), fn_o(a, b, 1.2, 0.8, 2.0, grad=grad)
+            got, ref = (got, ref) if grad else ((got,), (ref,))
+            for x, y in zip(got, ref):
+                assert x.shape == y.shape and np.all(np.isfinite(x)) and rel_err(x, y) <= TOL
+    K = rk.kff_C(F1, F2, 1.2, 0.8, 2.0)
+    assert np.all(K[0:3] == 0) and np.all(K[9:12] == 0) and np.all(K[21:24] == 0) and np.all(K[:, 6:9] == 0)
+    assert rel_err(dk.kff_C(F1, F2, 2.0, 1.5, 3.0), OD.kff_C(F1, F2, 2.0, 1.5, 3.0)) <= TOL
+    # a side with no groups at all
+    none = (np.zeros((0, d)), np.zeros((0, d, 3)), np.zeros(0, dtype=int), [])
+    assert rk.kff_C(none, F2, 1.2, 0.8, 2.0).shape == (0, 3 * len(F2[-1]))
+    assert rk.kff_C(F2, none, 1.2, 0.8, 2.0).shape == (3 * len(F2[-1]), 0)
+
+
+def test_properties_at_profiling_size():
+    """Size-independent properties on a real descriptor workload (100 x Cu32 from the device SO3, N = 9 700):
+    K = K^T, K(sigma) = sigma^2 K(1), dK/dl = central difference of K in l, diag mode = diagonal, and the
+    row-window build reproduces the one-pass build."""
+    from gpr_calculator_b200 import _lib, synthetic as syn
+    from gpr_calculator_b200.device import Pack, k_total_device, diag_device
+    from gpr_calculator_b200.SO3 import SO3
+    des = SO3(nmax=3, lmax=4, rcut=5.0)
+    E_dev, F_dev = syn.packed_from_batch(des, [a for a, _, _ in syn.structures(100, 2, 2000)])
+    e = Pack(E_dev[0], E_dev[1], E_dev[2])
+    f = Pack(F_dev[0], F_dev[2], F_dev[3], dxdr=F_dev[1])
+    NE, NF = e.n_groups, f.n_groups
+    sig, ell = 1.0, 0.1
+    K, dK = k_total_device(_lib.RBF, sig, ell, 2.0, (e, f), None, use_tol=False, grad=True)
+    N = NE + 3 * NF
+    assert K.shape == (N, N) and bool(torch.isfinite(K).all()) and bool(torch.isfinite(dK).all())
+    scale = K.abs().max().item()
+    assert (K - K.T).abs().max().item() <= 1e-13 * scale and (dK - dK.T).abs().max().item() <= 1e-13 * dK.abs().max().item()
+    K2, _ = k_total_device(_lib.RBF, 3.0 * sig, ell, 2.0, (e, f), None, use_tol=False, grad=False)
+    assert (K2 - 9.0 * K).abs().max().item() <= 1e-13 * 9.0 * scale
+    h = 1e-6
+    Kp, _ = k_total_device(_lib.RBF, sig, ell + h, 2.0, (e, f), None, use_tol=False, grad=False)
+    Km, _ = k_total_device(_lib.RBF, sig, ell - h, 2.0, (e, f), None, use_tol=False, grad=False)
+    fd = (Kp - Km) / (2 * h)
+    assert (fd - dK).abs().max().item() <= 1e-6 * dK.abs().max().item()
+    dg = diag_device(_lib.RBF, sig, ell, 2.0, (None, f), tol=0.0)
+    assert (dg - torch.diagonal(K)[NE:]).abs().max().item() <= 1e-13 * scale
+    w = ((10, 30), (700, 1500))
+    Kw, _ = k_total_device(_lib.RBF, sig, ell, 2.0, (e, f), None, use_tol=False, grad=False, window=w)
+    ref = torch.cat((K[10:30], K[NE + 3 * 700:NE + 3 * 1500]))
+    assert (Kw - ref).abs().max().item() <= 1e-13 * scale
