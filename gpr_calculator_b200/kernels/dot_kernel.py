@@ -9,10 +9,18 @@ def _host(t):
     return t.cpu().numpy()
 
 
+def _empty_block(p1, p2, r1, r2, n_out):
+    """A side without groups (an empty list / tuple) gives an empty block, like the reference's loops."""
+    shape = ((0 if p1 is None else p1.n_groups) * r1, (0 if p2 is None else p2.n_groups) * r2)
+    return np.zeros(shape) if n_out == 1 else tuple(np.zeros(shape) for _ in range(n_out))
+
+
 def kee_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False):
     """dot_kernel.py:9-63.  d/dsigma0 is the reference's constant 0.8*2*sigma^2*sigma0 (:58)."""
     require_cuda()
     e1, e2 = energy_pack(X1), energy_pack(X2)
+    if e1 is None or e2 is None:
+        return _empty_block(e1, e2, 1, 1, 3 if grad else 1)
     K = empty(e1.n_groups, e2.n_groups)
     _lib.call("gprb_kee", _lib.DOT, e1.handle, e2.handle, float(sigma), float(sigma0), float(zeta), 0, e1.n_groups,
               ptr(K), e2.n_groups, c_vp(0), 0, stream())
@@ -38,6 +46,9 @@ def kef_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False, tra
         C, Cs = _host(blocks[0]), _host(Cs.contiguous())
         return (C.T, Cs.T) if transpose else (C, Cs)
     e, f = energy_pack(X1), force_pack(X2)
+    if e is None or f is None:
+        out = _empty_block(e, f, 1, 3, 3 if grad else 1)
+        return (tuple(o.T for o in out) if grad else out.T) if transpose else out
     K = empty(e.n_groups, 3 * f.n_groups)
     _lib.call("gprb_kef", _lib.DOT, e.handle, f.handle, float(sigma), float(sigma0), float(zeta), 0, f.n_groups,
               ptr(K), 3 * f.n_groups, c_vp(0), 0, c_vp(0), 0, c_vp(0), 0, stream())
@@ -63,6 +74,8 @@ def kff_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False):
             blocks.append(K)
         return _host(blocks[0]), _host(interleave_stress(blocks[1], blocks[2], packs[0].n_groups))
     f1, f2 = force_pack(X1), force_pack(X2)
+    if f1 is None or f2 is None:
+        return _empty_block(f1, f2, 3, 3, 3 if grad else 1)
     K = empty(3 * f1.n_groups, 3 * f2.n_groups)
     _lib.call("gprb_kff", _lib.DOT, f1.handle, f2.handle, float(sigma), float(sigma0), float(zeta), 0, 0.0,
               _lib.FF_FULL, 0, f1.n_groups, ptr(K), 3 * f2.n_groups, c_vp(0), 0, stream())

@@ -3,7 +3,7 @@
 ``kee_C / kef_C / kff_C`` keep the reference signatures and return numpy arrays, so parity tests
 read like calls into the reference's cffi wrappers; the work is done by libgpr_b200.so.
 """
-import torch
+import numpy as np
 
 from .. import _lib
 from ..device import Pack, energy_pack, force_pack, stress_packs, interleave_stress, empty, ptr, stream, require_cuda, c_vp
@@ -13,10 +13,20 @@ def _host(t):
     return t.cpu().numpy()
 
 
+def _empty_block(p1, p2, r1, r2, n_out):
+    """A side without groups (an empty list / tuple) gives an empty block, like the reference's loops."""
+    if p1 is not None and p2 is not None:
+        return None
+    shape = ((0 if p1 is None else p1.n_groups) * r1, (0 if p2 is None else p2.n_groups) * r2)
+    return np.zeros(shape) if n_out == 1 else tuple(np.zeros(shape) for _ in range(n_out))
+
+
 def kee_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False):
     """Energy-energy block [m1, m2]; grad=True also returns dK/dsigma, dK/dl (rbf_kernel.py:7-85)."""
     require_cuda()
     e1, e2 = energy_pack(X1), energy_pack(X2)
+    if e1 is None or e2 is None:
+        return _empty_block(e1, e2, 1, 1, 3 if grad else 1)
     K = empty(e1.n_groups, e2.n_groups)
     dK = empty(e1.n_groups, e2.n_groups) if grad else None
     _lib.call("gprb_kee", _lib.RBF, e1.handle, e2.handle, float(sigma), float(l), float(zeta), 0, e1.n_groups,
@@ -45,6 +55,9 @@ def kef_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False, stress=False, transpos
         C, Cs = _host(blocks[0]), _host(Cs.contiguous())
         return (C.T, Cs.T) if transpose else (C, Cs)
     e, f = energy_pack(X1), force_pack(X2)
+    if e is None or f is None:
+        out = _empty_block(e, f, 1, 3, 3 if grad else 1)
+        return (tuple(o.T for o in out) if grad else out.T) if transpose else out
     K = empty(e.n_groups, 3 * f.n_groups)
     dK = empty(e.n_groups, 3 * f.n_groups) if grad else None
     _lib.call("gprb_kef", _lib.RBF, e.handle, f.handle, float(sigma), float(l), float(zeta), 0, f.n_groups,
@@ -75,6 +88,8 @@ def kff_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False, stress=False, diag=Fal
             blocks.append(K)
         return _host(blocks[0]), _host(interleave_stress(blocks[1], blocks[2], packs[0].n_groups))
     f1, f2 = force_pack(X1), force_pack(X2)
+    if f1 is None or f2 is None:
+        return _empty_block(f1, f2, 3, 3, 3 if grad else 1)
     K = empty(3 * f1.n_groups, 3 * f2.n_groups)
     dK = empty(3 * f1.n_groups, 3 * f2.n_groups) if grad else None
     _lib.call("gprb_kff", _lib.RBF, f1.handle, f2.handle, float(sigma), float(l), float(zeta),
