@@ -194,20 +194,46 @@ extern "C" int gprb_chol_factor(double *K, long long ldk, int N, void *stream) {
     GPRB_REQUIRE(K && N > 0, "gprb_chol_factor: bad argument");
     int rc = handles(st);
     if (rc) return rc;
-    int lwork = 0;
-    if (cusolverDnDpotrf_bufferSize(g_solver, CUBLAS_FILL_MODE_UPPER, N, K, (int)ldk, &lwork) != CUSOLVER_STATUS_SUCCESS) {
-        gprb_set_error("potrf_bufferSize failed"); return GPRB_ERR_CUDA;
-    }
-    double *work = nullptr; int *info = nullptr;
-    GPRB_CUDA(cudaMallocAsync((void **)&work, (size_t)(lwork > 0 ? lwork : 1) * sizeof(double), st));
-    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
-    cusolverStatus_t cs = cusolverDnDpotrf(g_solver, CUBLAS_FILL_MODE_UPPER, N, K, (int)ldk, work, lwork, info);
     int hinfo = -1;
-    GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
-    GPRB_CUDA(cudaFreeAsync(work, st));
-    GPRB_CUDA(cudaFreeAsync(info, st));
-    GPRB_CUDA(cudaStreamSynchronize(st));
-    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotrf status %d", (int)cs); return GPRB_ERR_CUDA; }
+    int *info = nullptr;
+    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
+    cusolverStatus_t cs;
+    if (getenv("GPRB_POTRF_LEGACY") == nullptr) {
+        // generic 64-bit interface: measured 374 ms against 444 ms of cusolverDnDpotrf at N = 32 980 on B200
+        // (tools/potrf_compare.py)
+        static cusolverDnParams_t params = nullptr;
+        if (!params && cusolverDnCreateParams(&params) != CUSOLVER_STATUS_SUCCESS) {
+            gprb_set_error("cusolverDnCreateParams failed"); return GPRB_ERR_CUDA;
+        }
+        size_t wdev = 0, whost = 0;
+        if (cusolverDnXpotrf_bufferSize(g_solver, params, CUBLAS_FILL_MODE_UPPER, (int64_t)N, CUDA_R_64F, K, (int64_t)ldk,
+                                        CUDA_R_64F, &wdev, &whost) != CUSOLVER_STATUS_SUCCESS) {
+            gprb_set_error("Xpotrf_bufferSize failed"); return GPRB_ERR_CUDA;
+        }
+        void *dwork = nullptr, *hwork = nullptr;
+        GPRB_CUDA(cudaMallocAsync(&dwork, wdev > 0 ? wdev : 8, st));
+        if (whost > 0) hwork = malloc(whost);
+        cs = cusolverDnXpotrf(g_solver, params, CUBLAS_FILL_MODE_UPPER, (int64_t)N, CUDA_R_64F, K, (int64_t)ldk, CUDA_R_64F,
+                              dwork, wdev, hwork, whost, info);
+        GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GPRB_CUDA(cudaFreeAsync(dwork, st));
+        GPRB_CUDA(cudaFreeAsync(info, st));
+        GPRB_CUDA(cudaStreamSynchronize(st));
+        free(hwork);
+    } else {
+        int lwork = 0;
+        if (cusolverDnDpotrf_bufferSize(g_solver, CUBLAS_FILL_MODE_UPPER, N, K, (int)ldk, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+            gprb_set_error("potrf_bufferSize failed"); return GPRB_ERR_CUDA;
+        }
+        double *work = nullptr;
+        GPRB_CUDA(cudaMallocAsync((void **)&work, (size_t)(lwork > 0 ? lwork : 1) * sizeof(double), st));
+        cs = cusolverDnDpotrf(g_solver, CUBLAS_FILL_MODE_UPPER, N, K, (int)ldk, work, lwork, info);
+        GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GPRB_CUDA(cudaFreeAsync(work, st));
+        GPRB_CUDA(cudaFreeAsync(info, st));
+        GPRB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolver potrf status %d", (int)cs); return GPRB_ERR_CUDA; }
     if (hinfo != 0) { gprb_set_error("matrix not positive definite (potrf info = %d)", hinfo); return GPRB_ERR_LINALG; }
     return GPRB_OK;
 }
