@@ -4,7 +4,8 @@ Only the pieces the covariance path needs are here: the ragged <-> packed layout
 (utilities.py:340-406), descriptor de-duplication (new_pt, :32-42), the conversion of a labelled
 structure into training rows (convert_train_data, :97-129), error metrics (:44-63, 81-85) and a
 symbol -> atomic-number table (stands in for pyxtal.database.element.Element, used at
-gaussianprocess.py:788,847).  Plotting, ASE-db and VASP helpers are out of scope.
+gaussianprocess.py:788,847), and the database readers that produce training rows (get_data, convert_struc,
+get_train_data, get_strucs, :132-246).  Plotting and VASP helpers are out of scope.
 """
 import numpy as np
 
@@ -140,6 +141,87 @@ def convert_train_data(data, des, N_force=100000):
 
 
 # ------------------------------------------------------------------------------------------------
+# database -> training rows (utilities.py:132-246): the input side of the path.  The ASE sqlite file is
+# read by asedb.py (no ASE needed); descriptors of all selected structures come from one batched device pass
+# when the descriptor offers calculate_batch (the reference loops des.calculate or forks a Pool, :207-224).
+# ------------------------------------------------------------------------------------------------
+def _rows(db_file):
+    from .asedb import read_rows
+    return read_rows(db_file)
+
+
+def get_train_data(db_file, include_stress=False):
+    """(structures, energies, forces[, stresses]) of every row (utilities.py:166-182)."""
+    strucs, energies, forces, stresses = [], [], [], []
+    for row in _rows(db_file):
+        strucs.append(row.toatoms())
+        energies.append(row.data["energy"])
+        forces.append(np.array(row.data["force"]))
+        if include_stress:
+            stresses.append(np.array(row.data["stress"]))
+    return (strucs, energies, forces, stresses) if include_stress else (strucs, energies, forces)
+
+
+def get_strucs(db_file, N_max=None):
+    """structures and (E, F, S or None) per row (utilities.py:225-241)."""
+    structures, values = [], []
+    for row in _rows(db_file):
+        structures.append(row.toatoms())
+        S = np.array(row.data["stress"]) if "stress" in row.data else None
+        values.append((row.data["energy"], np.array(row.data["force"]), S))
+        if N_max is not None and len(values) == N_max:
+            break
+    return structures, values
+
+
+def fea(des, struc):
+    return des.calculate(struc)
+
+
+def convert_struc(db_file, des, ids=None, N=None, ncpu=1, stress=False, batch=16):
+    """Descriptors and labels of the rows of a database (utilities.py:185-223): rows whose 0-based position is in
+    `ids` (all when None), at most N of them.  Returns (list of descriptor dicts, {'energy','forces','stress'}, structures).
+    `ncpu` is accepted for signature compatibility: the device pass replaces the process pool."""
+    structures, train_Y = [], {"energy": [], "forces": [], "stress": []}
+    for row in _rows(db_file):
+        if ids is not None and (row.id - 1) not in ids:
+            continue
+        train_Y["energy"].append(row.data["energy"])
+        train_Y["forces"].append(np.array(row.data["force"]))
+        if stress:
+            train_Y["stress"].append(np.array(row.data["stress"]))
+        structures.append(row.toatoms())
+        if N is not None and len(structures) == N:
+            break
+    if hasattr(des, "calculate_batch"):
+        xs = []
+        for s0 in range(0, len(structures), batch):
+            xs += des.calculate_batch(structures[s0:s0 + batch], to_host=True)
+    else:
+        xs = [des.calculate(struc) for struc in structures]
+    return xs, train_Y, structures
+
+
+def get_data(db_name, des, N_force=100000, lists=None, select=False, no_energy=False, ncpu=1):
+    """Training dict {'energy', 'force', 'db'} from a database (utilities.py:132-163): energy item (x, E / n_atoms, Z),
+    force item (x[seq[ids, 0]], dxdr[ids], F[i], Z[seq[ids, 0]]) with ids = argwhere(seq[:, 1] == i) for every atom i
+    (only atom 0 when select=True), at most N_force force items in total."""
+    X, Y, structures = convert_struc(db_name, des, lists, ncpu=ncpu)
+    energy_data, force_data, db_data = [], [], []
+    for k in range(len(X)):
+        ele = atomic_numbers(X[k]['elements'])
+        energy_data.append((X[k]['x'], Y["energy"][k] / len(X[k]['x']), ele))
+        f_ids = []
+        for i in ([0] if select else range(len(X[k]['x']))):
+            if len(force_data) < N_force:
+                x, dxdr, e = force_rows(X[k], ele, i)
+                force_data.append((x, dxdr, Y['forces'][k][i], e))
+                f_ids.append(i)
+        db_data.append((structures[k], Y['energy'][k], Y['forces'][k], True, f_ids))
+    return {"energy": [] if no_energy else energy_data, "force": force_data, "db": db_data}
+
+
+# ------------------------------------------------------------------------------------------------
 # error metrics (utilities.py:44-63, 81-85)
 # ------------------------------------------------------------------------------------------------
 def rmse(true, predicted):
@@ -158,6 +240,27 @@ def r2(true, predicted):
     true, predicted = np.array(true), np.array(predicted)
     mean = sum(true) / len(true)
     return 1 - sum((true - predicted) ** 2) / (sum((true - mean) ** 2) + 1e-8)
+
+
+def metrics(y_train, y_test, y_train_pred, y_test_pred, header):
+    """Two printed lines 'header Train[ n]: R2 .. MAE .. RMSE ..' (utilities.py:65-79)."""
+    out = []
+    for tag, y, yp in (("Train", y_train, y_train_pred), ("Test ", y_test, y_test_pred)):
+        r2_, mae_, rmse_ = metric_values(y, yp)
+        out.append("{:s} {:s}[{:4d}]: R2 {:6.4f} MAE {:6.3f} RMSE {:6.3f}".format(header, tag, len(y), r2_, mae_, rmse_))
+        print(out[-1])
+    return tuple(out)
+
+
+def metric_single(y_train, y_train_pred, header, show_max=False):
+    """One printed line (utilities.py:87-95; the reference formats the floats with '{:s}' and raises -- the values
+    are printed here the way `metrics` prints them)."""
+    r2_, mae_, rmse_ = metric_values(y_train, y_train_pred)
+    line = "{:s} [{:4d}]: R2 {:6.4f} MAE {:6.3f} RMSE {:6.3f}".format(header, len(y_train), r2_, mae_, rmse_)
+    if show_max:
+        line += '  Max {:6.4f}'.format(np.max(np.abs(np.asarray(y_train_pred) - np.asarray(y_train))))
+    print(line)
+    return line
 
 
 def metric_values(y, y_pred):

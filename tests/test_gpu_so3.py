@@ -92,3 +92,11 @@ def test_so3_options_vs_golden():
         r = SO3(**kw).calculate(at, atom_ids=list(g["s%d_ids" % k]))
         assert r["seq"].dtype == np.int64 and np.array_equal(r["seq"], g["s%d_sub_seq" % k])
         assert rel_err(r["x"], g["s%d_sub_x" % k]) <= 1e-10 and rel_err(r["dxdr"], g["s%d_sub_dxdr" % k]) <= 1e-10
+
+
+def test_get_data_from_database_on_device():
+    """utilities.get_data with the device descriptor (one batched pass over the database rows) against the
+    reference's own get_data output (tests/golden/getdata.*)."""
+    from test_host_logic import _check_get_data
+    from gpr_calculator_b200.SO3 import SO3
+    _check_get_data(SO3(nmax=3, lmax=4, rcut=5.0), 1e-10)

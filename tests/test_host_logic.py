@@ -247,3 +247,51 @@ def test_zero_build_targets_and_slab_pointers():
     assert bool((K.numpy()[must_zero] == 0).all())
     assert bool((K.numpy()[:NE] == 1).all())                # energy rows untouched
     assert slab_pointers([1000, 5000], 4, 2, 10) == [1000 + (4 * 10 + 2) * 8, 5000 + (4 * 10 + 2) * 8]
+
+
+def _check_get_data(des, tol):
+    """utilities.get_data / get_strucs / get_train_data / convert_struc against the reference's own output on the
+    committed 3-row database (tests/golden/gen_golden_getdata.py)."""
+    import os
+    from gpr_calculator_b200 import utilities as ut
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(gold, "getdata.npz"))
+    db = os.path.join(gold, "getdata.db")
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        cases = {"all": ut.get_data(db, des), "cap": ut.get_data(db, des, N_force=17),
+                 "sel": ut.get_data(db, des, lists=[0, 2], select=True), "noe": ut.get_data(db, des, N_force=5, no_energy=True)}
+    for name, data in cases.items():
+        assert len(data["energy"]) == int(g[name + "_nE"]) and len(data["force"]) == int(g[name + "_nF"])
+        assert [len(x) for x, _, _, _ in data["force"]] == list(g[name + "_F_rows"])
+        assert [len(f) for _, _, _, _, f in data["db"]] == list(g[name + "_db_fids"])
+        assert np.array_equal(np.array([y for _, _, y, _ in data["force"]]), g[name + "_F_y"])
+        Fx = np.concatenate([x for x, _, _, _ in data["force"]])
+        Fd = np.concatenate([d for _, d, _, _ in data["force"]])
+        if name == "all":
+            assert abs(np.abs(Fx).sum() - g["all_F_x_abs_sum"]) <= tol * g["all_F_x_abs_sum"]
+            assert abs(np.abs(Fd).sum() - g["all_F_dxdr_abs_sum"]) <= tol * g["all_F_dxdr_abs_sum"]
+            continue
+        assert np.abs(Fx - g[name + "_F_x"]).max() <= tol * np.abs(g[name + "_F_x"]).max()
+        assert np.abs(Fd - g[name + "_F_dxdr"]).max() <= tol * np.abs(g[name + "_F_dxdr"]).max()
+        assert np.array_equal(np.concatenate([e for _, _, _, e in data["force"]]), g[name + "_F_ele"])
+        assert np.array_equal(np.array([E for _, E, _, _, _ in data["db"]]), g[name + "_db_E"])
+        if data["energy"]:
+            Ex = np.concatenate([x for x, _, _ in data["energy"]])
+            assert np.abs(Ex - g[name + "_E_x"]).max() <= tol * np.abs(g[name + "_E_x"]).max()
+            assert np.array_equal(np.array([y for _, y, _ in data["energy"]]), g[name + "_E_y"])
+            assert np.array_equal(np.concatenate([e for _, _, e in data["energy"]]), g[name + "_E_ele"])
+    S, V = ut.get_strucs(db, N_max=2)
+    assert len(S) == int(g["strucs_n"]) and np.array_equal(np.array([v[0] for v in V]), g["strucs_E"]) and V[0][2] is None
+    strucs, energies, forces = ut.get_train_data(db)
+    assert len(strucs) == 3 and np.array_equal(np.array(energies)[:2], g["strucs_E"]) and forces[0].shape == (13, 3)
+    xs, Y, st = ut.convert_struc(db, des, ids=[1], N=1)
+    assert len(xs) == 1 and len(st) == 1 and Y["energy"] == [energies[1]]
+    assert "R2" in ut.metric_single(np.arange(5.0), np.arange(5.0) + 0.1, "Energy", show_max=True)
+    assert len(ut.metrics(np.arange(5.0), np.arange(3.0), np.arange(5.0), np.arange(3.0), "F")) == 2
+
+
+def test_get_data_with_oracle_descriptor():
+    from oracle import so3 as oso3
+    _check_get_data(oso3.SO3Oracle(3, 4, 5.0, 2.0), 1e-10)
