@@ -199,8 +199,8 @@ extern "C" int gprb_chol_factor(double *K, long long ldk, int N, void *stream) {
     GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
     cusolverStatus_t cs;
     if (getenv("GPRB_POTRF_LEGACY") == nullptr) {
-        // generic 64-bit interface: measured 374 ms against 444 ms of cusolverDnDpotrf at N = 32 980 on B200
-        // (tools/potrf_compare.py)
+        // generic 64-bit interface (same speed as cusolverDnDpotrf at N = 32 980 on B200: 445 ms; the library's LOWER
+        // fill mode takes 374 ms, tools/potrf_compare.py -- a switch of the stored triangle left for the next round)
         static cusolverDnParams_t params = nullptr;
         if (!params && cusolverDnCreateParams(&params) != CUSOLVER_STATUS_SUCCESS) {
             gprb_set_error("cusolverDnCreateParams failed"); return GPRB_ERR_CUDA;

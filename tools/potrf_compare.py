@@ -14,7 +14,10 @@ A = torch.randn((N, 2048), dtype=torch.float64, device="cuda", generator=g)
 K0 = A @ A.T
 K0 += N * torch.eye(N, dtype=torch.float64, device="cuda")
 del A
-for name in ("gprb_chol_factor", "torch.linalg.cholesky_ex(upper=False)", "torch.linalg.cholesky_ex(upper=True)"):
+names = ("gprb_chol_factor", "torch.linalg.cholesky_ex(upper=False)", "torch.linalg.cholesky_ex(upper=True)")
+if len(sys.argv) > 2 and sys.argv[2] == "lib":
+    names = names[:1]
+for name in names:
     ts = []
     for it in range(3):
         K = K0.clone()
