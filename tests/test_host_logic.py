@@ -295,3 +295,46 @@ def _check_get_data(des, tol):
 def test_get_data_with_oracle_descriptor():
     from oracle import so3 as oso3
     _check_get_data(oso3.SO3Oracle(3, 4, 5.0, 2.0), 1e-10)
+
+
+def test_inverse_rows_gradient_algebra_in_numpy():
+    """The blocked route of GP._lml_gradient_rows restated in numpy: 1/2 tr((alpha alpha^T - K^-1) dK) from trailing-block
+    solves only (K^-1[r0:r1, r0:] per block, K^-1[0:NE, :] for the energy columns), with the sharded-row semantics of the
+    trace kernel (energy rows: E-E part on / right of the diagonal doubled; force rows: 2 x F-E + F-F on / right of the
+    diagonal doubled), equals the dense formula of gaussianprocess.py:188-198."""
+    from scipy.linalg import solve_triangular
+    from gpr_calculator_b200.gaussianprocess import _row_pieces
+    rng = np.random.default_rng(12)
+    NE, N = 5, 61
+    A = rng.normal(size=(N, N))
+    K = A @ A.T + N * np.eye(N)
+    B = rng.normal(size=(N, N))
+    dK = B + B.T
+    alpha = rng.normal(size=N)
+    W = np.outer(alpha, alpha) - np.linalg.inv(K)
+    want = 0.5 * np.sum(W * dK)
+    L = np.linalg.cholesky(K)
+
+    def inverse_rows(r0, r1, c0):
+        LT = L[c0:, c0:]
+        E = np.zeros((N - c0, r1 - r0))
+        E[np.arange(r0 - c0, r1 - c0), np.arange(r1 - r0)] = 1.0
+        Y = solve_triangular(LT, E, lower=True)
+        return solve_triangular(LT.T, Y, lower=False).T              # [r1 - r0, N - c0]
+
+    Einv = inverse_rows(0, NE, 0)
+    got = 0.0
+    # two "ranks": their row ranges together cover every row once, like dist.row_windows
+    for ranges in ([(0, 2), (NE, NE + 21)], [(2, NE), (NE + 21, N)]):
+        for (r0, r1, _) in _row_pieces(ranges, NE, N, parts=4, min_rows=4):
+            rows = Einv[r0:r1] if r1 <= NE else inverse_rows(r0, r1, r0)
+            c0 = 0 if r1 <= NE else r0
+            for i in range(r0, r1):
+                jend = NE if i < NE else N
+                for j in range(i, jend):
+                    w = alpha[i] * alpha[j] - rows[i - r0, j - c0]
+                    got += (0.5 if j == i else 1.0) * w * dK[i, j]
+                if i >= NE:
+                    for j in range(NE):
+                        got += (alpha[i] * alpha[j] - Einv[j, i]) * dK[i, j]
+    assert abs(got - want) <= 1e-10 * abs(want)
