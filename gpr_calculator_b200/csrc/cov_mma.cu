@@ -31,8 +31,10 @@
 //    Row groups that continue in a neighbouring CTA are combined with fp64 atomics into the
 //    pre-zeroed output (two addends: still order independent).
 #include "common.cuh"
+#pragma nv_diag_suppress 128   // the 4x4-block path below the two-stage branch is unreachable in the two-stage instantiations
 #include <cstdint>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -58,6 +60,7 @@ struct CovParams {
     // fused all-gather (gprb_kff_multi / gprb_kfe_multi): every finished value of K is also stored into the
     // same slab of n_extra peer matrices (NVLink peer stores, pointers from gprb_peer_open); dK stays local
     double *Kx[GPRB_MAX_DST - 1]; int n_extra;
+    int two_stage;                                            // experimental two-stage contraction (no-gradient K_ff)
 };
 
 __constant__ double c_exp2_tab[32];    // 2^(j/32)
@@ -167,7 +170,52 @@ __device__ __forceinline__ void pair_weights(const CovParams &P, const double *t
     }
 }
 
-template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI>
+// Flush of the per-thread sums `out[NT]` when column group J is complete: transposing butterfly over the 4 lanes of a
+// row, segmented suffix sum over the 8 rows of the warp, head rows to flush buffer flush_idx & 3, one mbarrier arrival per
+// warp; the final sums of flush k are taken two flushes later (finish).  A macro so that the 4x4-block path and the
+// two-stage path expand the very same statements.
+#define COV_FLUSH_GROUP(J) \
+    do { \
+                if (flush_idx >= 2) finish(flush_idx - 2, J2); \
+                const int fb = flush_idx & (NFB - 1); \
+                const bool b0 = lane & 1, b1 = lane & 2; \
+                double wv[N1], zv[N2]; \
+_Pragma("unroll") \
+                for (int i = 0; i < N1; i++) { \
+                    const double lo = out[2 * i], hi = (2 * i + 1 < NT) ? out[(2 * i + 1 < NT) ? 2 * i + 1 : 0] : 0.0; \
+                    const double keep = b0 ? hi : lo, send = b0 ? lo : hi; \
+                    wv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1); \
+                } \
+_Pragma("unroll") \
+                for (int i = 0; i < N2; i++) { \
+                    const double lo = wv[2 * i], hi = (2 * i + 1 < N1) ? wv[(2 * i + 1 < N1) ? 2 * i + 1 : 0] : 0.0; \
+                    const double keep = b1 ? hi : lo, send = b1 ? lo : hi; \
+                    zv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); \
+                } \
+_Pragma("unroll") \
+                for (int i = 0; i < N2; i++) { \
+                    double tv = __shfl_down_sync(0xffffffffu, zv[i], 4); \
+                    zv[i] += p1 ? tv : 0.0; \
+                    tv = __shfl_down_sync(0xffffffffu, zv[i], 8); \
+                    zv[i] += p2 ? tv : 0.0; \
+                    tv = __shfl_down_sync(0xffffffffu, zv[i], 16); \
+                    zv[i] += p4 ? tv : 0.0; \
+                } \
+                if (is_head) { \
+                    double *dst = sRow + (size_t)(fb * MAXROWS + arow_local) * NT + q4; \
+_Pragma("unroll") \
+                    for (int i = 0; i < N2; i++) \
+                        if (4 * i + q4 < NT) dst[4 * i] = zv[i]; \
+                } \
+_Pragma("unroll") \
+                for (int i = 0; i < NT; i++) out[i] = 0.0; \
+                __syncwarp(); \
+                if (lane == 0) mbar_arrive(&barFlush[fb]); \
+                J2 = J1; J1 = J; \
+                flush_idx++; \
+    } while (0)
+
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI, bool TWO>
 __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) {
     constexpr bool FF = (NB == 4);
     constexpr int NOUT = FF ? 9 : 3;
@@ -253,6 +301,11 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
     double out[NT];
 #pragma unroll
     for (int i = 0; i < NT; i++) out[i] = 0.0;
+    double Z[TWO ? 3 : 1][TWO ? 4 : 1][2];      // two-stage path: Z_e[ra][8 t + 2 q4 + {0, 1}] of the current column group
+#pragma unroll
+    for (int e = 0; e < (TWO ? 3 : 1); e++)
+#pragma unroll
+        for (int t = 0; t < (TWO ? 4 : 1); t++) { Z[e][t][0] = 0.0; Z[e][t][1] = 0.0; }
     int flush_idx = 0, J1 = 0, J2 = 0;      // J1 / J2: column groups of the previous two flushes
 
     // Final sums of flush kk (column group J): every warp adds the per-warp partials of ITS share of the
@@ -333,6 +386,80 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
             const int *rec = sRec + (buf * CH + tt) * REC;
             const double *pb = sB + (size_t)(buf * CH + tt) * b_tile_d + lane;
 
+            if constexpr (TWO) {
+                // EXPERIMENTAL two-stage contraction (GPRB_KFF_TWO_STAGE=1; no gradient, d in 29..32; not yet run on a GPU --
+                // profiles/experiments/README.md and two_stage_emulation.py).  Stage 1: x^(a) . [x^; B~_e](b) -> s, q_e
+                // (32 DMMAs).  Stage 2, per column segment: Z_e[a, :] += W1 B~_e + (W2 q_e) x^ with the stage-1 accumulator
+                // registers as A fragments (k order b = 2 q4 + j) and the B fragments read from the same slabs (48 DMMAs).
+                // Per column group: out_ce = A~_c(a) . Z_e(a), then the common flush.
+                static_assert(!TWO || (NB == 4 && KS_T == 8 && !GRAD), "two-stage path: K_ff without gradient, 8 k-steps");
+                double a1[4][2];
+#pragma unroll
+                for (int e = 0; e < 4; e++) { a1[e][0] = 0.0; a1[e][1] = 0.0; }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const double af = pa[k * 32];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) dmma(a1[e][0], a1[e][1], af, pb[(e * 8 + k) * 32]);
+                }
+                const int2 eb2 = *reinterpret_cast<const int2 *>(rec + 2 * q4);
+                double tw1[2], tw2[2];
+                bool tvalid[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int ele_b = j ? eb2.y : eb2.x;
+                    tvalid[j] = (ele_a == ele_b) && (ele_a >= 0);
+                    double du1 = 0.0, du2 = 0.0;
+                    tw2[j] = 0.0;
+                    pair_weights<KERNEL, false, true, ZI>(P, sTab, a1[0][j], tvalid[j], tw1[j], tw2[j], du1, du2);
+                }
+                const double *pbt = pb - lane;                      // tile base: stage 2 addresses the slabs by (row b, column)
+                const int nseg2 = rec[8];
+                for (int sg = 0; sg < nseg2; sg++) {
+                    const int J = rec[10 + 2 * sg], mf = rec[11 + 2 * sg];
+                    if (J < ga || J >= gb) continue;
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const bool on = tvalid[j] && ((mf >> (2 * q4 + j)) & 1);
+                        const double W1 = on ? tw1[j] : 0.0;
+                        double V[3];
+#pragma unroll
+                        for (int e = 0; e < 3; e++) V[e] = on ? tw2[j] * a1[1 + e][j] : 0.0;
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            // B fragment of n-tile t: element (k = q4 -> row b = 2 q4 + j, n = ra -> column 8 t + ra)
+                            const int off = (2 * t + (ra >> 2)) * 32 + (2 * q4 + j) * 4 + (ra & 3);
+                            const double bx = pbt[off];
+#pragma unroll
+                            for (int e = 0; e < 3; e++) {
+                                dmma(Z[e][t][0], Z[e][t][1], W1, pbt[(1 + e) * 8 * 32 + off]);
+                                dmma(Z[e][t][0], Z[e][t][1], V[e], bx);
+                            }
+                        }
+                    }
+                    if (!(mf & 0x100)) continue;
+                    // column group J is complete: out_ce = sum over this thread's 8 columns of A~_c[ra, col] Z_e[ra, col]
+                    const double *par = pa - lane;                  // row tile base (component c + 1 holds A~_c)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            // columns 8 t + 2 q4 + {0, 1}: k-step 2 t + (q4 >> 1), kk = 2 (q4 & 1) + {0, 1} (adjacent: one 16-byte read)
+                            const double2 av = *reinterpret_cast<const double2 *>(
+                                par + ((c + 1) * 8 + 2 * t + (q4 >> 1)) * 32 + ra * 4 + 2 * (q4 & 1));
+#pragma unroll
+                            for (int e = 0; e < 3; e++) out[c * 3 + e] = fma(av.x, Z[e][t][0], fma(av.y, Z[e][t][1], out[c * 3 + e]));
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 3; e++)
+#pragma unroll
+                        for (int t = 0; t < 4; t++) { Z[e][t][0] = 0.0; Z[e][t][1] = 0.0; }
+                    COV_FLUSH_GROUP(J);
+                }
+                continue;
+            }
+
             double acc[4][NB][2];
 #pragma unroll
             for (int c = 0; c < 4; c++)
@@ -412,44 +539,7 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                 }
                 if (!(mf & 0x100)) continue;
 
-                // ---- flush: column group J is complete -------------------------------------------------
-                if (flush_idx >= 2) finish(flush_idx - 2, J2);      // my share of the sums of two flushes ago
-                const int fb = flush_idx & (NFB - 1);
-                const bool b0 = lane & 1, b1 = lane & 2;
-                double wv[N1], zv[N2];
-#pragma unroll
-                for (int i = 0; i < N1; i++) {
-                    const double lo = out[2 * i], hi = (2 * i + 1 < NT) ? out[(2 * i + 1 < NT) ? 2 * i + 1 : 0] : 0.0;
-                    const double keep = b0 ? hi : lo, send = b0 ? lo : hi;
-                    wv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-                }
-#pragma unroll
-                for (int i = 0; i < N2; i++) {
-                    const double lo = wv[2 * i], hi = (2 * i + 1 < N1) ? wv[(2 * i + 1 < N1) ? 2 * i + 1 : 0] : 0.0;
-                    const double keep = b1 ? hi : lo, send = b1 ? lo : hi;
-                    zv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);      // row sum of value 4*i + q4
-                }
-#pragma unroll
-                for (int i = 0; i < N2; i++) {   // segmented suffix sum over the 8 rows: total lands on the head row
-                    double tv = __shfl_down_sync(0xffffffffu, zv[i], 4);
-                    zv[i] += p1 ? tv : 0.0;
-                    tv = __shfl_down_sync(0xffffffffu, zv[i], 8);
-                    zv[i] += p2 ? tv : 0.0;
-                    tv = __shfl_down_sync(0xffffffffu, zv[i], 16);
-                    zv[i] += p4 ? tv : 0.0;
-                }
-                if (is_head) {
-                    double *dst = sRow + (size_t)(fb * MAXROWS + arow_local) * NT + q4;
-#pragma unroll
-                    for (int i = 0; i < N2; i++)
-                        if (4 * i + q4 < NT) dst[4 * i] = zv[i];
-                }
-#pragma unroll
-                for (int i = 0; i < NT; i++) out[i] = 0.0;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&barFlush[fb]);          // release: this warp's partials of flush k are in place
-                J2 = J1; J1 = J;
-                flush_idx++;
+                COV_FLUSH_GROUP(J);      // column group J is complete
             }
         }
         // release the stage; the warp that arrives last refills it
@@ -526,9 +616,9 @@ int upload_tables() {
     return GPRB_OK;
 }
 
-template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI>
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI, bool TWO = false>
 int launch_cov_m(const CovParams &P, int n_blocks, cudaStream_t st) {
-    auto kern = cov_mma_kernel<NB, KS_T, KERNEL, GRAD, ZI, MULTI>;
+    auto kern = cov_mma_kernel<NB, KS_T, KERNEL, GRAD, ZI, MULTI, TWO>;
     static bool configured = false;
     if (!configured) {
         GPRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_smem_bytes(NB, GPRB_MAX_KS, GRAD)));
@@ -544,6 +634,11 @@ int launch_cov_m(const CovParams &P, int n_blocks, cudaStream_t st) {
 // the single-destination kernels carry no peer-store code at all (MULTI = false)
 template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI>
 int launch_cov(const CovParams &P, int n_blocks, cudaStream_t st) {
+    if constexpr (NB == 4 && KS_T == 8 && !GRAD) {
+        if (P.two_stage)      // experimental, opt-in (GPRB_KFF_TWO_STAGE=1)
+            return P.n_extra > 0 ? launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, true, true>(P, n_blocks, st)
+                                 : launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, false, true>(P, n_blocks, st);
+    }
     return P.n_extra > 0 ? launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, true>(P, n_blocks, st)
                          : launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, false>(P, n_blocks, st);
 }
@@ -642,6 +737,7 @@ static int kff_impl(int kernel, const gprb_pack *f1_, const gprb_pack *f2, doubl
     P.K = K; P.ldk = ldk; P.dK = dK; P.lddk = lddk;
     P.n_extra = n_dst - 1;
     for (int p = 1; p < n_dst; p++) P.Kx[p - 1] = K_dst[p];
+    P.two_stage = (getenv("GPRB_KFF_TWO_STAGE") != nullptr && !dK && mode != GPRB_FF_DIAG) ? 1 : 0;
     P.n_splits = mode == GPRB_FF_DIAG ? 1 : choose_splits(f1->sched_n, f2->n_groups);
     return dispatch_cov<4>(kernel, dK != nullptr, P, f1->sched_n, st);
 }

@@ -365,3 +365,29 @@ def test_properties_at_profiling_size():
     Kw, _ = k_total_device(_lib.RBF, sig, ell, 2.0, (e, f), None, use_tol=False, grad=False, window=w)
     ref = torch.cat((K[10:30], K[NE + 3 * 700:NE + 3 * 1500]))
     assert (Kw - ref).abs().max().item() <= 1e-13 * scale
+
+
+@pytest.mark.skipif(os.environ.get("GPRB_TEST_TWO_STAGE", "0") in ("", "0"),
+                    reason="experimental two-stage K_ff path (GPRB_KFF_TWO_STAGE=1): opt-in until it has been run on a GPU")
+def test_two_stage_path_matches_block_path(monkeypatch):
+    """The experimental two-stage contraction against the production 4x4-block kernel: ragged groups, three species,
+    pair cut, full / symmetric / upper modes, RBF and Dot."""
+    from gpr_calculator_b200 import _lib
+    from gpr_calculator_b200.device import Pack, k_total_device
+    from gpr_calculator_b200.utilities import list_to_tuple
+    rng = np.random.default_rng(21)
+    X, dX, ELE, ind = list_to_tuple(make_force(rng, 37, lo=3, hi=40, species=(1, 16, 46), zero_rows=1))
+    f = Pack(X, ELE, ind, dxdr=dX)
+    X2, dX2, ELE2, ind2 = list_to_tuple(make_force(rng, 23, lo=1, hi=70, species=(1, 16, 46)))
+    f2 = Pack(X2, ELE2, ind2, dxdr=dX2)
+    for kern, p1, zeta in ((_lib.RBF, 0.7, 2.0), (_lib.RBF, 0.4, 3.0), (_lib.DOT, 1.1, 2.0)):
+        for side2, sym, tol in ((None, True, 1e-10), (None, False, 1e-10), ((None, f2), False, 1e-3)):
+            out = {}
+            for two in ("", "1"):
+                if two:
+                    monkeypatch.setenv("GPRB_KFF_TWO_STAGE", "1")
+                else:
+                    monkeypatch.delenv("GPRB_KFF_TWO_STAGE", raising=False)
+                out[two], _ = k_total_device(kern, 1.3, p1, zeta, (None, f), side2, use_tol=True, tol=tol, grad=False, symmetric=sym)
+            scale = out[""].abs().max().item()
+            assert (out["1"] - out[""]).abs().max().item() <= 1e-12 * scale
