@@ -35,6 +35,20 @@ int handles(cudaStream_t st) {
     return GPRB_OK;
 }
 
+// Which triangle holds the Cholesky factor.  Default: CUBLAS_FILL_MODE_UPPER on the column-major view (the factor L in the
+// row-major lower triangle).  GPRB_POTRF_LOWER=1 (experimental, opt-in: cuSOLVER's potrf is 16 % faster in that mode at
+// N = 32 980, tools/potrf_compare.py; not yet run on a GPU) stores L^T in the row-major upper triangle instead; every
+// consumer of the factor below takes the mode from here, and GP.L_ reads the same switch.
+bool factor_lower() {
+    static const bool lower = getenv("GPRB_POTRF_LOWER") != nullptr;
+    return lower;
+}
+cublasFillMode_t factor_uplo() { return factor_lower() ? CUBLAS_FILL_MODE_LOWER : CUBLAS_FILL_MODE_UPPER; }
+// the two triangular solves of (factor factor^T) X = B, first and second
+cublasOperation_t solve_op(int step) {
+    return factor_lower() ? (step == 0 ? CUBLAS_OP_N : CUBLAS_OP_T) : (step == 0 ? CUBLAS_OP_T : CUBLAS_OP_N);
+}
+
 __global__ void add_noise_kernel(double *K, long long ld, int N, int NE, double ne2, double nf2) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N) K[(long long)i * ld + i] += (i < NE) ? ne2 : nf2;
@@ -206,14 +220,14 @@ extern "C" int gprb_chol_factor(double *K, long long ldk, int N, void *stream) {
             gprb_set_error("cusolverDnCreateParams failed"); return GPRB_ERR_CUDA;
         }
         size_t wdev = 0, whost = 0;
-        if (cusolverDnXpotrf_bufferSize(g_solver, params, CUBLAS_FILL_MODE_UPPER, (int64_t)N, CUDA_R_64F, K, (int64_t)ldk,
+        if (cusolverDnXpotrf_bufferSize(g_solver, params, factor_uplo(), (int64_t)N, CUDA_R_64F, K, (int64_t)ldk,
                                         CUDA_R_64F, &wdev, &whost) != CUSOLVER_STATUS_SUCCESS) {
             gprb_set_error("Xpotrf_bufferSize failed"); return GPRB_ERR_CUDA;
         }
         void *dwork = nullptr, *hwork = nullptr;
         GPRB_CUDA(cudaMallocAsync(&dwork, wdev > 0 ? wdev : 8, st));
         if (whost > 0) hwork = malloc(whost);
-        cs = cusolverDnXpotrf(g_solver, params, CUBLAS_FILL_MODE_UPPER, (int64_t)N, CUDA_R_64F, K, (int64_t)ldk, CUDA_R_64F,
+        cs = cusolverDnXpotrf(g_solver, params, factor_uplo(), (int64_t)N, CUDA_R_64F, K, (int64_t)ldk, CUDA_R_64F,
                               dwork, wdev, hwork, whost, info);
         GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
         GPRB_CUDA(cudaFreeAsync(dwork, st));
@@ -222,12 +236,12 @@ extern "C" int gprb_chol_factor(double *K, long long ldk, int N, void *stream) {
         free(hwork);
     } else {
         int lwork = 0;
-        if (cusolverDnDpotrf_bufferSize(g_solver, CUBLAS_FILL_MODE_UPPER, N, K, (int)ldk, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+        if (cusolverDnDpotrf_bufferSize(g_solver, factor_uplo(), N, K, (int)ldk, &lwork) != CUSOLVER_STATUS_SUCCESS) {
             gprb_set_error("potrf_bufferSize failed"); return GPRB_ERR_CUDA;
         }
         double *work = nullptr;
         GPRB_CUDA(cudaMallocAsync((void **)&work, (size_t)(lwork > 0 ? lwork : 1) * sizeof(double), st));
-        cs = cusolverDnDpotrf(g_solver, CUBLAS_FILL_MODE_UPPER, N, K, (int)ldk, work, lwork, info);
+        cs = cusolverDnDpotrf(g_solver, factor_uplo(), N, K, (int)ldk, work, lwork, info);
         GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
         GPRB_CUDA(cudaFreeAsync(work, st));
         GPRB_CUDA(cudaFreeAsync(info, st));
@@ -245,7 +259,7 @@ extern "C" int gprb_chol_solve_vec(const double *L, long long ldl, int N, double
     if (rc) return rc;
     int *info = nullptr;
     GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
-    cusolverStatus_t cs = cusolverDnDpotrs(g_solver, CUBLAS_FILL_MODE_UPPER, N, 1, L, (int)ldl, b, N, info);
+    cusolverStatus_t cs = cusolverDnDpotrs(g_solver, factor_uplo(), N, 1, L, (int)ldl, b, N, info);
     GPRB_CUDA(cudaFreeAsync(info, st));
     if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotrs status %d", (int)cs); return GPRB_ERR_CUDA; }
     return GPRB_OK;
@@ -271,9 +285,9 @@ extern "C" int gprb_chol_inverse(const double *L, long long ldl, int N, double *
         GPRB_LAUNCHED();
         const double one = 1.0;
         // column-major view: K = U^T U with U in the upper triangle of L's buffer;  U^T Y = I, then U X = Y
-        cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+        cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(0), CUBLAS_DIAG_NON_UNIT,
                                            (int64_t)N, (int64_t)N, &one, L, (int64_t)ldl, Kinv, (int64_t)ldi);
-        cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+        cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(1), CUBLAS_DIAG_NON_UNIT,
                                            (int64_t)N, (int64_t)N, &one, L, (int64_t)ldl, Kinv, (int64_t)ldi);
         if (b1 != CUBLAS_STATUS_SUCCESS || b2 != CUBLAS_STATUS_SUCCESS) {
             gprb_set_error("cublasDtrsm_64 status %d / %d", (int)b1, (int)b2); return GPRB_ERR_CUDA;
@@ -286,18 +300,19 @@ extern "C" int gprb_chol_inverse(const double *L, long long ldl, int N, double *
     GPRB_CUDA(cudaMemcpy2DAsync(Kinv, ldi * sizeof(double), L, ldl * sizeof(double), (size_t)N * sizeof(double), N,
                                 cudaMemcpyDeviceToDevice, st));
     int lwork = 0;
-    if (cusolverDnDpotri_bufferSize(g_solver, CUBLAS_FILL_MODE_UPPER, N, Kinv, (int)ldi, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+    if (cusolverDnDpotri_bufferSize(g_solver, factor_uplo(), N, Kinv, (int)ldi, &lwork) != CUSOLVER_STATUS_SUCCESS) {
         gprb_set_error("potri_bufferSize failed"); return GPRB_ERR_CUDA;
     }
     double *work = nullptr; int *info = nullptr;
     GPRB_CUDA(cudaMallocAsync((void **)&work, (size_t)(lwork > 0 ? lwork : 1) * sizeof(double), st));
     GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
-    cusolverStatus_t cs = cusolverDnDpotri(g_solver, CUBLAS_FILL_MODE_UPPER, N, Kinv, (int)ldi, work, lwork, info);
+    cusolverStatus_t cs = cusolverDnDpotri(g_solver, factor_uplo(), N, Kinv, (int)ldi, work, lwork, info);
     GPRB_CUDA(cudaFreeAsync(work, st));
     GPRB_CUDA(cudaFreeAsync(info, st));
     if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotri status %d", (int)cs); return GPRB_ERR_CUDA; }
     dim3 grid((N + 31) / 32, (N + 31) / 32), block(32, 32);
-    mirror_lower_kernel<<<grid, block, 0, st>>>(Kinv, ldi, N);
+    if (factor_lower()) mirror_upper_kernel<<<grid, block, 0, st>>>(Kinv, ldi, N);      // potri filled the row-major upper triangle
+    else mirror_lower_kernel<<<grid, block, 0, st>>>(Kinv, ldi, N);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
@@ -392,9 +407,9 @@ extern "C" int gprb_chol_inverse_rows(const double *L, long long ldl, int N, int
     // column-major view, K_T = U^T U with U in the upper triangle of the factor's buffer;  U^T Y = E, then U X = Y
     const double one = 1.0;
     const double *U = L + (long long)c0 * ldl + c0;
-    cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+    cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(0), CUBLAS_DIAG_NON_UNIT,
                                        (int64_t)n, (int64_t)nrhs, &one, U, (int64_t)ldl, out, (int64_t)ldo);
-    cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+    cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(1), CUBLAS_DIAG_NON_UNIT,
                                        (int64_t)n, (int64_t)nrhs, &one, U, (int64_t)ldl, out, (int64_t)ldo);
     if (b1 != CUBLAS_STATUS_SUCCESS || b2 != CUBLAS_STATUS_SUCCESS) {
         gprb_set_error("cublasDtrsm_64 (inverse rows) status %d / %d", (int)b1, (int)b2); return GPRB_ERR_CUDA;
@@ -480,7 +495,7 @@ extern "C" int gprb_predict_chol(int m, int N, const double *Ks, long long ldks,
     GPRB_CUDA(cudaMemcpy2DAsync(work, (size_t)N * sizeof(double), Ks, (size_t)ldks * sizeof(double), (size_t)N * sizeof(double), m,
                                 cudaMemcpyDeviceToDevice, st));
     const double one = 1.0;
-    cublasStatus_t bs = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+    cublasStatus_t bs = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(0), CUBLAS_DIAG_NON_UNIT,
                                        (int64_t)N, (int64_t)m, &one, L, (int64_t)ldl, work, (int64_t)N);
     if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDtrsm_64 (predict) status %d", (int)bs); return GPRB_ERR_CUDA; }
     predict_rows_chol_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, work, diag, mean, var);

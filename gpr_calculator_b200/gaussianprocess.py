@@ -50,6 +50,9 @@ def _zero_build_targets(K, NE, chunks=16):
         K[r:r + per, r:].zero_()
 
 
+_FACTOR_LOWER = os.environ.get("GPRB_POTRF_LOWER") is not None      # read once, like the library does
+
+
 def _row_pieces(r_ranges, NE, N, parts=16, min_rows=512):
     """Blocks of rows for the inverse-rows likelihood gradient: the row ranges a rank holds (their rows of dK
     stored one range after the other) cut at the energy / force boundary and, for force rows, into blocks of
@@ -161,11 +164,16 @@ class GP():
     def L_(self):
         if self._L_dev is None:
             return None
-        return np.tril(self._L_dev.cpu().numpy())
+        M = self._L_dev.cpu().numpy()
+        # the factor lives in the row-major lower triangle; with the experimental GPRB_POTRF_LOWER=1 (gp_linalg.cu) it is
+        # L^T in the upper one
+        return np.triu(M).T.copy() if _FACTOR_LOWER else np.tril(M)
 
     @L_.setter
     def L_(self, v):
-        self._L_dev = None if v is None else torch.as_tensor(np.asarray(v, dtype=np.float64), device="cuda").contiguous()
+        if v is not None and _FACTOR_LOWER:
+            v = np.asarray(v, dtype=np.float64).T
+        self._L_dev = None if v is None else torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64), device="cuda").contiguous()
 
     @property
     def _K_inv(self):
