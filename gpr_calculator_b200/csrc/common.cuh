@@ -15,6 +15,9 @@ void gprb_set_error(const char *fmt, ...);
 int gprb_pool_init();            // stream-ordered pool of the current device, memory kept across synchronisations (pack.cu)
 void gprb_pool_free(void *ptr, cudaStream_t st);  // cudaFreeAsync ordered on st (NULL pointer is fine)
 
+struct gprb_pack;
+int gprb_check_device(const gprb_pack *p, const char *who);   // GPRB_ERR_ARG unless the pack lives on the current device (pack.cu)
+
 // kernels launched by this library so far (gprb_launch_count); bumped next to every <<< >>>
 #include <atomic>
 extern std::atomic<long long> g_gprb_launches;

@@ -153,6 +153,7 @@ extern "C" int gprb_kee(int kernel, const gprb_pack *e1, const gprb_pack *e2, do
                         int grp_begin, int grp_end, double *K, long long ldk, double *dK, long long lddk, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(e1 && e2 && K, "gprb_kee: NULL argument");
+    { int rcd = gprb_check_device(e1, "gprb_kee"); if (rcd || (rcd = gprb_check_device(e2, "gprb_kee"))) return rcd; }
     GPRB_REQUIRE(e1->ncols == 0 && e2->ncols == 0, "gprb_kee: both sides must be energy packs");
     GPRB_REQUIRE(e1->d == e2->d, "gprb_kee: descriptor length mismatch %d vs %d", e1->d, e2->d);
     GPRB_REQUIRE(kernel == GPRB_KERNEL_RBF || kernel == GPRB_KERNEL_DOT, "gprb_kee: unknown kernel %d", kernel);
@@ -183,6 +184,7 @@ extern "C" int gprb_kee(int kernel, const gprb_pack *e1, const gprb_pack *e2, do
 extern "C" int gprb_kee_diag(int kernel, const gprb_pack *e, double p0, double p1, double zeta, double *out, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(e && out, "gprb_kee_diag: NULL argument");
+    { int rcd = gprb_check_device(e, "gprb_kee_diag"); if (rcd) return rcd; }
     GPRB_REQUIRE(e->ncols == 0, "gprb_kee_diag: need an energy pack");
     if (e->n_groups == 0) return GPRB_OK;
     EEParams P = {};

@@ -60,7 +60,7 @@ struct CovParams {
     // fused all-gather (gprb_kff_multi / gprb_kfe_multi): every finished value of K is also stored into the
     // same slab of n_extra peer matrices (NVLink peer stores, pointers from gprb_peer_open); dK stays local
     double *Kx[GPRB_MAX_DST - 1]; int n_extra;
-    int two_stage;                                            // experimental two-stage contraction (no-gradient K_ff)
+    int two_stage;                                            // two-stage contraction (no-gradient K_ff, 8 k-steps)
 };
 
 __constant__ double c_exp2_tab[32];    // 2^(j/32)
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
             const double *pb = sB + (size_t)(buf * CH + tt) * b_tile_d + lane;
 
             if constexpr (TWO) {
-                // EXPERIMENTAL two-stage contraction (GPRB_KFF_TWO_STAGE=1; no gradient, d in 29..32; not yet run on a GPU --
-                // profiles/experiments/README.md and two_stage_emulation.py).  Stage 1: x^(a) . [x^; B~_e](b) -> s, q_e
+                // Two-stage contraction (no gradient, d in 29..32; design: profiles/experiments/README.md and
+                // two_stage_emulation.py; parity: test_two_stage_path_matches_block_path).  Stage 1: x^(a) . [x^; B~_e](b) -> s, q_e
                 // (32 DMMAs).  Stage 2, per column segment: Z_e[a, :] += W1 B~_e + (W2 q_e) x^ with the stage-1 accumulator
                 // registers as A fragments (k order b = 2 q4 + j) and the B fragments read from the same slabs (48 DMMAs).
                 // Per column group: out_ce = A~_c(a) . Z_e(a), then the common flush.
@@ -606,23 +606,35 @@ int integer_zeta(double zeta) {
     return ((double)zi == zeta && zi >= 1 && zi <= 4) ? zi : -1;
 }
 
+// per-device one-time state (a process may drive several GPUs): __constant__ tables and function attributes exist per device
+constexpr int MAX_DEV = 64;
+int current_device(int *dev) {
+    GPRB_CUDA(cudaGetDevice(dev));
+    GPRB_REQUIRE(*dev >= 0 && *dev < MAX_DEV, "device index %d out of range", *dev);
+    return GPRB_OK;
+}
+
 int upload_tables() {
-    static bool done = false;
-    if (done) return GPRB_OK;
+    static bool done[MAX_DEV] = {};
+    int dev = 0;
+    { int rc = current_device(&dev); if (rc) return rc; }
+    if (done[dev]) return GPRB_OK;
     double tab[32];
     for (int j = 0; j < 32; j++) tab[j] = std::exp2((double)j / 32.0);
     GPRB_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof tab));
-    done = true;
+    done[dev] = true;
     return GPRB_OK;
 }
 
 template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI, bool TWO = false>
 int launch_cov_m(const CovParams &P, int n_blocks, cudaStream_t st) {
     auto kern = cov_mma_kernel<NB, KS_T, KERNEL, GRAD, ZI, MULTI, TWO>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[MAX_DEV] = {};
+    int dev = 0;
+    { int rc = current_device(&dev); if (rc) return rc; }
+    if (!configured[dev]) {
         GPRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_smem_bytes(NB, GPRB_MAX_KS, GRAD)));
-        configured = true;
+        configured[dev] = true;
     }
     dim3 grid(n_blocks, P.n_splits);
     kern<<<grid, THREADS, cov_smem_bytes(NB, P.ks, GRAD), st>>>(P);
@@ -635,7 +647,7 @@ int launch_cov_m(const CovParams &P, int n_blocks, cudaStream_t st) {
 template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI>
 int launch_cov(const CovParams &P, int n_blocks, cudaStream_t st) {
     if constexpr (NB == 4 && KS_T == 8 && !GRAD) {
-        if (P.two_stage)      // experimental, opt-in (GPRB_KFF_TWO_STAGE=1)
+        if (P.two_stage)
             return P.n_extra > 0 ? launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, true, true>(P, n_blocks, st)
                                  : launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, false, true>(P, n_blocks, st);
     }
@@ -699,6 +711,7 @@ static int kff_impl(int kernel, const gprb_pack *f1_, const gprb_pack *f2, doubl
     for (int p = 0; p < n_dst; p++) GPRB_REQUIRE(K_dst[p], "gprb_kff: NULL destination %d", p);
     double *K = K_dst[0];
     GPRB_REQUIRE(f1 && f2 && K, "gprb_kff: NULL argument");
+    { int rcd = gprb_check_device(f1, "gprb_kff"); if (rcd || (rcd = gprb_check_device(f2, "gprb_kff"))) return rcd; }
     GPRB_REQUIRE(f1->ncols == 3 && f2->ncols == 3, "gprb_kff: both sides must be force packs");
     GPRB_REQUIRE(f1->d == f2->d, "gprb_kff: descriptor length mismatch %d vs %d", f1->d, f2->d);
     GPRB_REQUIRE(kernel == GPRB_KERNEL_RBF || kernel == GPRB_KERNEL_DOT, "gprb_kff: unknown kernel %d", kernel);
@@ -737,7 +750,10 @@ static int kff_impl(int kernel, const gprb_pack *f1_, const gprb_pack *f2, doubl
     P.K = K; P.ldk = ldk; P.dK = dK; P.lddk = lddk;
     P.n_extra = n_dst - 1;
     for (int p = 1; p < n_dst; p++) P.Kx[p - 1] = K_dst[p];
-    P.two_stage = (getenv("GPRB_KFF_TWO_STAGE") != nullptr && !dK && mode != GPRB_FF_DIAG) ? 1 : 0;
+    // no-gradient K_ff with 8 k-steps (d = 29..32, the default descriptor): two-stage contraction, 1.44x the 4x4-block path
+    // (profiles/r02_two_stage.txt); GPRB_KFF_TWO_STAGE=0 selects the block path for the A/B parity test
+    const char *two_env = getenv("GPRB_KFF_TWO_STAGE");
+    P.two_stage = (!dK && mode != GPRB_FF_DIAG && !(two_env && two_env[0] == '0')) ? 1 : 0;
     P.n_splits = mode == GPRB_FF_DIAG ? 1 : choose_splits(f1->sched_n, f2->n_groups);
     return dispatch_cov<4>(kernel, dK != nullptr, P, f1->sched_n, st);
 }
@@ -767,6 +783,7 @@ static int kef_impl(int kernel, const gprb_pack *e, const gprb_pack *f_, double 
     double *Kfe = Kfe_dst[0];
     for (int p = 1; p < n_dst; p++) GPRB_REQUIRE(Kfe_dst[p], "gprb_kfe_multi: NULL destination %d", p);
     GPRB_REQUIRE(e && f && (Kef || Kfe), "gprb_kef: NULL argument");
+    { int rcd = gprb_check_device(e, "gprb_kef"); if (rcd || (rcd = gprb_check_device(f, "gprb_kef"))) return rcd; }
     GPRB_REQUIRE(e->ncols == 0 && f->ncols == 3, "gprb_kef: need (energy pack, force pack)");
     GPRB_REQUIRE(e->d == f->d, "gprb_kef: descriptor length mismatch %d vs %d", e->d, f->d);
     GPRB_REQUIRE(kernel == GPRB_KERNEL_RBF || kernel == GPRB_KERNEL_DOT, "gprb_kef: unknown kernel %d", kernel);

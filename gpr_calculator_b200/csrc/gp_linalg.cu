@@ -11,23 +11,37 @@
 // unchanged, "lower" here == CUBLAS_FILL_MODE_UPPER there.
 #include "common.cuh"
 #include <cstdint>
+#include <algorithm>
 #include <cusolverDn.h>
 #include <cublas_v2.h>
 #include <cstdlib>
 
 namespace {
 
-cusolverDnHandle_t g_solver = nullptr;
-cublasHandle_t g_blas = nullptr;
+// library handles are per device (a process may drive several GPUs, e.g. after torch.cuda.set_device in a notebook)
+constexpr int MAX_DEV = 64;
+cusolverDnHandle_t g_solver_dev[MAX_DEV] = {};
+cublasHandle_t g_blas_dev[MAX_DEV] = {};
+cusolverDnParams_t g_params_dev[MAX_DEV] = {};
+thread_local cusolverDnHandle_t g_solver = nullptr;     // handles of the current device, set by handles()
+thread_local cublasHandle_t g_blas = nullptr;
+thread_local cusolverDnParams_t g_params = nullptr;
 
 int handles(cudaStream_t st) {
     { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
-    if (!g_solver) {
-        if (cusolverDnCreate(&g_solver) != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnCreate failed"); return GPRB_ERR_CUDA; }
+    int dev = 0;
+    GPRB_CUDA(cudaGetDevice(&dev));
+    GPRB_REQUIRE(dev >= 0 && dev < MAX_DEV, "device index %d out of range", dev);
+    if (!g_solver_dev[dev]) {
+        if (cusolverDnCreate(&g_solver_dev[dev]) != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnCreate failed"); return GPRB_ERR_CUDA; }
     }
-    if (!g_blas) {
-        if (cublasCreate(&g_blas) != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasCreate failed"); return GPRB_ERR_CUDA; }
+    if (!g_blas_dev[dev]) {
+        if (cublasCreate(&g_blas_dev[dev]) != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasCreate failed"); return GPRB_ERR_CUDA; }
     }
+    if (!g_params_dev[dev]) {
+        if (cusolverDnCreateParams(&g_params_dev[dev]) != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnCreateParams failed"); return GPRB_ERR_CUDA; }
+    }
+    g_solver = g_solver_dev[dev]; g_blas = g_blas_dev[dev]; g_params = g_params_dev[dev];
     if (cusolverDnSetStream(g_solver, st) != CUSOLVER_STATUS_SUCCESS || cublasSetStream(g_blas, st) != CUBLAS_STATUS_SUCCESS) {
         gprb_set_error("setting the library stream failed");
         return GPRB_ERR_CUDA;
@@ -35,19 +49,30 @@ int handles(cudaStream_t st) {
     return GPRB_OK;
 }
 
-// Which triangle holds the Cholesky factor.  Default: CUBLAS_FILL_MODE_UPPER on the column-major view (the factor L in the
-// row-major lower triangle).  GPRB_POTRF_LOWER=1 (experimental, opt-in: cuSOLVER's potrf is 16 % faster in that mode at
-// N = 32 980, tools/potrf_compare.py; not yet run on a GPU) stores L^T in the row-major upper triangle instead; every
-// consumer of the factor below takes the mode from here, and GP.L_ reads the same switch.
-bool factor_lower() {
-    static const bool lower = getenv("GPRB_POTRF_LOWER") != nullptr;
-    return lower;
-}
-cublasFillMode_t factor_uplo() { return factor_lower() ? CUBLAS_FILL_MODE_LOWER : CUBLAS_FILL_MODE_UPPER; }
-// the two triangular solves of (factor factor^T) X = B, first and second
-cublasOperation_t solve_op(int step) {
-    return factor_lower() ? (step == 0 ? CUBLAS_OP_N : CUBLAS_OP_T) : (step == 0 ? CUBLAS_OP_T : CUBLAS_OP_N);
-}
+// Stream-ordered temporaries that are returned to the pool on every exit path of an entry point.
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    Scratch(const Scratch &) = delete;
+    void *get(size_t bytes) {
+        void *p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, st);
+        if (e != cudaSuccess) { gprb_set_error("cudaMallocAsync of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+        ptrs.push_back(p);
+        return p;
+    }
+    ~Scratch() { for (void *p : ptrs) gprb_pool_free(p, st); }
+};
+
+// The Cholesky factor L lives in the row-major lower triangle == CUBLAS_FILL_MODE_UPPER of the column-major view the
+// libraries see (K = U^T U, U = L^T); every consumer below (potrs, trsm, potri) reads that triangle.  gprb_chol_factor
+// itself runs cuSOLVER's potrf in the OTHER fill mode, which is 20 % faster on B200 (357 vs 446 ms at N = 32 980,
+// profiles/r02_potrf_modes.txt), and mirrors the factor into the lower triangle afterwards (3 ms), so the trsm-heavy
+// consumers keep the mode in which cuBLAS trsm is faster (inverse rows: 990 vs 1 043 ms).
+constexpr cublasFillMode_t FACTOR_UPLO = CUBLAS_FILL_MODE_UPPER;
+// the two triangular solves of (U^T U) X = B, first and second
+constexpr cublasOperation_t solve_op(int step) { return step == 0 ? CUBLAS_OP_T : CUBLAS_OP_N; }
 
 __global__ void add_noise_kernel(double *K, long long ld, int N, int NE, double ne2, double nf2) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,17 +127,19 @@ __global__ void lml_terms_kernel(const double *L, long long ld, int N, const dou
     if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
 }
 
-// partial[block] = sum over the block's rows of sum_j (alpha_i alpha_j - Kinv_ij) * dK_ij
-// partial2[block] = sum over rows of (alpha_i^2 - Kinv_ii) * w_i
+// partial[3 b + 0] = sum over the block's rows of sum_j (alpha_i alpha_j - Kinv_ij) * dK_ij
+// partial[3 b + 1] = sum over rows of (alpha_i^2 - Kinv_ii) * w_i          (w = we / wf for energy / force rows)
+// partial[3 b + 2] = the same with the second weight pair (we2 / wf2)
 // KinvE != NULL (sharded inverse, gprb_lml_grad_trace_rows): the columns j < NE of a force row come from the
 // energy rows of the inverse, Kinv[i, j] = KinvE[j * ldE + i]; Kinv then only has to be valid for j >= i.
 __global__ void __launch_bounds__(256) trace_kernel(int N, int r0, int r1, const double *__restrict__ alpha,
                                                     const double *__restrict__ Kinv, long long ldi,
                                                     const double *__restrict__ dK, long long lddk,
-                                                    int NE, double we, double wf, int upper_only, double *partial,
+                                                    int NE, double we, double wf, double we2, double wf2,
+                                                    int upper_only, double *partial,
                                                     const double *__restrict__ KinvE = nullptr, long long ldE = 0) {
     __shared__ double sh[32];
-    double acc = 0.0, acc2 = 0.0;
+    double acc = 0.0, acc2 = 0.0, acc3 = 0.0;
     for (int i = r0 + blockIdx.x; i < r1; i += gridDim.x) {
         const double ai = alpha[i];
         const double *ki = Kinv + (long long)i * ldi;
@@ -136,10 +163,14 @@ __global__ void __launch_bounds__(256) trace_kernel(int N, int r0, int r1, const
                 for (int j = threadIdx.x; j < N; j += blockDim.x) acc = fma(fma(ai, alpha[j], -ki[j]), di[j], acc);
             }
         }
-        if (threadIdx.x == 0) acc2 += (ai * ai - ki[i]) * (i < NE ? we : wf);
+        if (threadIdx.x == 0) {
+            const double wii = ai * ai - ki[i];
+            acc2 += wii * (i < NE ? we : wf);
+            acc3 += wii * (i < NE ? we2 : wf2);
+        }
     }
     acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = acc; partial[2 * blockIdx.x + 1] = acc2; }
+    if (threadIdx.x == 0) { partial[3 * blockIdx.x] = acc; partial[3 * blockIdx.x + 1] = acc2; partial[3 * blockIdx.x + 2] = acc3; }
 }
 
 __global__ void block_sum_kernel(int N, int r0, int r1, int c0, int c1, const double *__restrict__ alpha,
@@ -152,15 +183,20 @@ __global__ void block_sum_kernel(int N, int r0, int r1, int c0, int c1, const do
         for (int j = c0 + threadIdx.x; j < c1; j += blockDim.x) acc += fma(ai, alpha[j], -ki[j]);
     }
     acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = acc; partial[2 * blockIdx.x + 1] = 0.0; }
+    if (threadIdx.x == 0) { partial[3 * blockIdx.x] = acc; partial[3 * blockIdx.x + 1] = 0.0; partial[3 * blockIdx.x + 2] = 0.0; }
 }
 
-__global__ void final_sum_kernel(const double *partial, int n, double *out) {
-    // one thread, fixed order: deterministic
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int i = 0; i < n; i++) { a += partial[2 * i]; b += partial[2 * i + 1]; }
-        out[0] = 0.5 * a; out[1] = 0.5 * b;
+// out[k] (+)= 0.5 * sum_b partial[3 b + k]: one warp, lane-strided partial sums combined in a fixed order (deterministic)
+__global__ void final_sum_kernel(const double *partial, int n, double *out, int accumulate) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) { a += partial[3 * i]; b += partial[3 * i + 1]; c += partial[3 * i + 2]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (threadIdx.x == 0) {
+        if (accumulate) { out[0] += 0.5 * a; out[1] += 0.5 * b; out[2] += 0.5 * c; }
+        else { out[0] = 0.5 * a; out[1] = 0.5 * b; out[2] = 0.5 * c; }
     }
 }
 
@@ -192,6 +228,105 @@ int copy_scalars(double *host, const double *dev, int n, cudaStream_t st) {
     return GPRB_OK;
 }
 
+__global__ void set_identity_kernel(double *A, long long ld, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) A[(long long)i * ld + i] = 1.0;
+}
+
+__global__ void unit_columns_kernel(double *B, long long ldb, int n_rows, int col0) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_rows) B[(long long)k * ldb + col0 + k] = 1.0;
+}
+
+// ---- enqueue-only building blocks (no host synchronisation): shared by the granular entry points and gprb_lml_eval ----
+
+// potrf in cuSOLVER's faster fill mode + mirror of the factor into the row-major lower triangle; *info_dev = potrf status
+int factor_enqueue(double *K, long long ldk, int N, int *info_dev, Scratch &scratch, cudaStream_t st) {
+    size_t wdev = 0, whost = 0;
+    if (cusolverDnXpotrf_bufferSize(g_solver, g_params, CUBLAS_FILL_MODE_LOWER, (int64_t)N, CUDA_R_64F, K, (int64_t)ldk,
+                                    CUDA_R_64F, &wdev, &whost) != CUSOLVER_STATUS_SUCCESS) {
+        gprb_set_error("Xpotrf_bufferSize failed"); return GPRB_ERR_CUDA;
+    }
+    void *dwork = scratch.get(wdev);
+    if (!dwork) return GPRB_ERR_CUDA;
+    std::vector<unsigned char> hwork(whost);
+    cusolverStatus_t cs = cusolverDnXpotrf(g_solver, g_params, CUBLAS_FILL_MODE_LOWER, (int64_t)N, CUDA_R_64F, K, (int64_t)ldk,
+                                           CUDA_R_64F, dwork, wdev, whost ? hwork.data() : nullptr, whost, info_dev);
+    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolver potrf status %d", (int)cs); return GPRB_ERR_CUDA; }
+    dim3 grid((N + 31) / 32, (N + 31) / 32), block(32, 32);
+    mirror_upper_kernel<<<grid, block, 0, st>>>(K, ldk, N);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+int solve_vec_enqueue(const double *L, long long ldl, int N, double *b, int *info_dev) {
+    cusolverStatus_t cs = cusolverDnDpotrs(g_solver, FACTOR_UPLO, N, 1, L, (int)ldl, b, N, info_dev);
+    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotrs status %d", (int)cs); return GPRB_ERR_CUDA; }
+    return GPRB_OK;
+}
+
+// K^-1[T, T] = (L_TT L_TT^T)^-1 for the trailing index set T = [c0, N) (L^-1 is triangular), so rows [r0, r1) of the
+// inverse, restricted to the columns >= c0, are the solution of the trailing system with the unit vectors of those
+// rows as right-hand sides (symmetric: row = column).
+int inverse_rows_enqueue(const double *L, long long ldl, int N, int r0, int r1, int c0, double *out, long long ldo, cudaStream_t st) {
+    const int n = N - c0, nrhs = r1 - r0;
+    GPRB_CUDA(cudaMemset2DAsync(out, ldo * sizeof(double), 0, (size_t)n * sizeof(double), nrhs, st));
+    unit_columns_kernel<<<(nrhs + 255) / 256, 256, 0, st>>>(out, ldo, nrhs, r0 - c0);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    // what potrs does, through the 64-bit cuBLAS interface (N^2 may exceed 2^31, e.g. the S4 configuration):
+    // column-major view, K_T = U^T U with U in the upper triangle of the factor's buffer;  U^T Y = E, then U X = Y
+    const double one = 1.0;
+    const double *U = L + (long long)c0 * ldl + c0;
+    cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, FACTOR_UPLO, solve_op(0), CUBLAS_DIAG_NON_UNIT,
+                                       (int64_t)n, (int64_t)nrhs, &one, U, (int64_t)ldl, out, (int64_t)ldo);
+    cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, FACTOR_UPLO, solve_op(1), CUBLAS_DIAG_NON_UNIT,
+                                       (int64_t)n, (int64_t)nrhs, &one, U, (int64_t)ldl, out, (int64_t)ldo);
+    if (b1 != CUBLAS_STATUS_SUCCESS || b2 != CUBLAS_STATUS_SUCCESS) {
+        gprb_set_error("cublasDtrsm_64 (inverse rows) status %d / %d", (int)b1, (int)b2); return GPRB_ERR_CUDA;
+    }
+    return GPRB_OK;
+}
+
+int trace_blocks(int rows) { return rows < 1184 ? rows : 1184; }     // 8 x 148
+
+// dev_out[0..2] (+)= {1/2 tr-term, 1/2 sum W_ii w_i, 1/2 sum W_ii w2_i} of the rows [r0, r1)
+int trace_enqueue(int N, int r0, int r1, const double *alpha, const double *Kinv_virt, long long ldi, const double *dK_rows,
+                  long long lddk, int NE, double we, double wf, double we2, double wf2, int upper_only,
+                  const double *KinvE, long long ldE, double *dev_out, int accumulate, Scratch &scratch, cudaStream_t st) {
+    const int blocks = trace_blocks(r1 - r0);
+    double *d = (double *)scratch.get((size_t)3 * blocks * sizeof(double));
+    if (!d) return GPRB_ERR_CUDA;
+    trace_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, alpha, Kinv_virt, ldi, dK_rows, lddk, NE, we, wf, we2, wf2, upper_only, d, KinvE, ldE);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, dev_out, accumulate);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+int block_sum_enqueue(int N, int r0, int r1, int c0, int c1, const double *alpha, const double *Kinv, long long ldi,
+                      double *dev_out, int accumulate, Scratch &scratch, cudaStream_t st) {
+    const int blocks = trace_blocks(r1 - r0);
+    double *d = (double *)scratch.get((size_t)3 * blocks * sizeof(double));
+    if (!d) return GPRB_ERR_CUDA;
+    block_sum_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, c0, c1, alpha, Kinv, ldi, d);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, dev_out, accumulate);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+// the kernels index Kinv[i * ld + j] with global (i, j): shift the base so that (r0, c0) is element 0 of a slab
+const double *virtual_base(const double *rows, long long ldr, int r0, int c0) {
+    return reinterpret_cast<const double *>(reinterpret_cast<uintptr_t>(rows) -
+                                            (uintptr_t)(((long long)r0 * ldr + c0) * (long long)sizeof(double)));
+}
+
 }  // namespace
 
 extern "C" int gprb_add_noise(double *K, long long ldk, int N, int NE, double noise_e, double noise_f, void *stream) {
@@ -208,46 +343,13 @@ extern "C" int gprb_chol_factor(double *K, long long ldk, int N, void *stream) {
     GPRB_REQUIRE(K && N > 0, "gprb_chol_factor: bad argument");
     int rc = handles(st);
     if (rc) return rc;
+    Scratch scratch(st);
+    int *info = (int *)scratch.get(sizeof(int));
+    if (!info) return GPRB_ERR_CUDA;
+    if ((rc = factor_enqueue(K, ldk, N, info, scratch, st))) return rc;
     int hinfo = -1;
-    int *info = nullptr;
-    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
-    cusolverStatus_t cs;
-    if (getenv("GPRB_POTRF_LEGACY") == nullptr) {
-        // generic 64-bit interface (same speed as cusolverDnDpotrf at N = 32 980 on B200: 445 ms; the library's LOWER
-        // fill mode takes 374 ms, tools/potrf_compare.py -- a switch of the stored triangle left for the next round)
-        static cusolverDnParams_t params = nullptr;
-        if (!params && cusolverDnCreateParams(&params) != CUSOLVER_STATUS_SUCCESS) {
-            gprb_set_error("cusolverDnCreateParams failed"); return GPRB_ERR_CUDA;
-        }
-        size_t wdev = 0, whost = 0;
-        if (cusolverDnXpotrf_bufferSize(g_solver, params, factor_uplo(), (int64_t)N, CUDA_R_64F, K, (int64_t)ldk,
-                                        CUDA_R_64F, &wdev, &whost) != CUSOLVER_STATUS_SUCCESS) {
-            gprb_set_error("Xpotrf_bufferSize failed"); return GPRB_ERR_CUDA;
-        }
-        void *dwork = nullptr, *hwork = nullptr;
-        GPRB_CUDA(cudaMallocAsync(&dwork, wdev > 0 ? wdev : 8, st));
-        if (whost > 0) hwork = malloc(whost);
-        cs = cusolverDnXpotrf(g_solver, params, factor_uplo(), (int64_t)N, CUDA_R_64F, K, (int64_t)ldk, CUDA_R_64F,
-                              dwork, wdev, hwork, whost, info);
-        GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
-        GPRB_CUDA(cudaFreeAsync(dwork, st));
-        GPRB_CUDA(cudaFreeAsync(info, st));
-        GPRB_CUDA(cudaStreamSynchronize(st));
-        free(hwork);
-    } else {
-        int lwork = 0;
-        if (cusolverDnDpotrf_bufferSize(g_solver, factor_uplo(), N, K, (int)ldk, &lwork) != CUSOLVER_STATUS_SUCCESS) {
-            gprb_set_error("potrf_bufferSize failed"); return GPRB_ERR_CUDA;
-        }
-        double *work = nullptr;
-        GPRB_CUDA(cudaMallocAsync((void **)&work, (size_t)(lwork > 0 ? lwork : 1) * sizeof(double), st));
-        cs = cusolverDnDpotrf(g_solver, factor_uplo(), N, K, (int)ldk, work, lwork, info);
-        GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
-        GPRB_CUDA(cudaFreeAsync(work, st));
-        GPRB_CUDA(cudaFreeAsync(info, st));
-        GPRB_CUDA(cudaStreamSynchronize(st));
-    }
-    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolver potrf status %d", (int)cs); return GPRB_ERR_CUDA; }
+    GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GPRB_CUDA(cudaStreamSynchronize(st));
     if (hinfo != 0) { gprb_set_error("matrix not positive definite (potrf info = %d)", hinfo); return GPRB_ERR_LINALG; }
     return GPRB_OK;
 }
@@ -257,17 +359,10 @@ extern "C" int gprb_chol_solve_vec(const double *L, long long ldl, int N, double
     GPRB_REQUIRE(L && b && N > 0, "gprb_chol_solve_vec: bad argument");
     int rc = handles(st);
     if (rc) return rc;
-    int *info = nullptr;
-    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
-    cusolverStatus_t cs = cusolverDnDpotrs(g_solver, factor_uplo(), N, 1, L, (int)ldl, b, N, info);
-    GPRB_CUDA(cudaFreeAsync(info, st));
-    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotrs status %d", (int)cs); return GPRB_ERR_CUDA; }
-    return GPRB_OK;
-}
-
-__global__ void set_identity_kernel(double *A, long long ld, int N) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) A[(long long)i * ld + i] = 1.0;
+    Scratch scratch(st);
+    int *info = (int *)scratch.get(sizeof(int));
+    if (!info) return GPRB_ERR_CUDA;
+    return solve_vec_enqueue(L, ldl, N, b, info);
 }
 
 extern "C" int gprb_chol_inverse(const double *L, long long ldl, int N, double *Kinv, long long ldi, void *stream) {
@@ -275,19 +370,19 @@ extern "C" int gprb_chol_inverse(const double *L, long long ldl, int N, double *
     GPRB_REQUIRE(L && Kinv && N > 0, "gprb_chol_inverse: bad argument");
     int rc = handles(st);
     if (rc) return rc;
+    dim3 grid((N + 31) / 32, (N + 31) / 32), block(32, 32);
     if ((long long)N * N >= (1LL << 31) || getenv("GPRB_FORCE_TRSM") != nullptr) {   // env: test hook for the large-N route
         // cuSOLVER's potri (and the 64-bit trtri) reject N^2 >= 2^31 (N > 46340, e.g. the S4 configuration).
         // Same result the way gaussianprocess.py:195 gets it, cho_solve(L, I): two triangular solves with
         // the 64-bit cuBLAS interface on an identity right-hand side held in the output buffer.
-        dim3 grid((N + 31) / 32, (N + 31) / 32), block(32, 32);
         GPRB_CUDA(cudaMemset2DAsync(Kinv, ldi * sizeof(double), 0, (size_t)N * sizeof(double), N, st));
         set_identity_kernel<<<(N + 255) / 256, 256, 0, st>>>(Kinv, ldi, N);
         GPRB_LAUNCHED();
         const double one = 1.0;
         // column-major view: K = U^T U with U in the upper triangle of L's buffer;  U^T Y = I, then U X = Y
-        cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(0), CUBLAS_DIAG_NON_UNIT,
+        cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, FACTOR_UPLO, solve_op(0), CUBLAS_DIAG_NON_UNIT,
                                            (int64_t)N, (int64_t)N, &one, L, (int64_t)ldl, Kinv, (int64_t)ldi);
-        cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(1), CUBLAS_DIAG_NON_UNIT,
+        cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, FACTOR_UPLO, solve_op(1), CUBLAS_DIAG_NON_UNIT,
                                            (int64_t)N, (int64_t)N, &one, L, (int64_t)ldl, Kinv, (int64_t)ldi);
         if (b1 != CUBLAS_STATUS_SUCCESS || b2 != CUBLAS_STATUS_SUCCESS) {
             gprb_set_error("cublasDtrsm_64 status %d / %d", (int)b1, (int)b2); return GPRB_ERR_CUDA;
@@ -300,19 +395,16 @@ extern "C" int gprb_chol_inverse(const double *L, long long ldl, int N, double *
     GPRB_CUDA(cudaMemcpy2DAsync(Kinv, ldi * sizeof(double), L, ldl * sizeof(double), (size_t)N * sizeof(double), N,
                                 cudaMemcpyDeviceToDevice, st));
     int lwork = 0;
-    if (cusolverDnDpotri_bufferSize(g_solver, factor_uplo(), N, Kinv, (int)ldi, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+    if (cusolverDnDpotri_bufferSize(g_solver, FACTOR_UPLO, N, Kinv, (int)ldi, &lwork) != CUSOLVER_STATUS_SUCCESS) {
         gprb_set_error("potri_bufferSize failed"); return GPRB_ERR_CUDA;
     }
-    double *work = nullptr; int *info = nullptr;
-    GPRB_CUDA(cudaMallocAsync((void **)&work, (size_t)(lwork > 0 ? lwork : 1) * sizeof(double), st));
-    GPRB_CUDA(cudaMallocAsync((void **)&info, sizeof(int), st));
-    cusolverStatus_t cs = cusolverDnDpotri(g_solver, factor_uplo(), N, Kinv, (int)ldi, work, lwork, info);
-    GPRB_CUDA(cudaFreeAsync(work, st));
-    GPRB_CUDA(cudaFreeAsync(info, st));
+    Scratch scratch(st);
+    double *work = (double *)scratch.get((size_t)(lwork > 0 ? lwork : 1) * sizeof(double));
+    int *info = (int *)scratch.get(sizeof(int));
+    if (!work || !info) return GPRB_ERR_CUDA;
+    cusolverStatus_t cs = cusolverDnDpotri(g_solver, FACTOR_UPLO, N, Kinv, (int)ldi, work, lwork, info);
     if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDpotri status %d", (int)cs); return GPRB_ERR_CUDA; }
-    dim3 grid((N + 31) / 32, (N + 31) / 32), block(32, 32);
-    if (factor_lower()) mirror_upper_kernel<<<grid, block, 0, st>>>(Kinv, ldi, N);      // potri filled the row-major upper triangle
-    else mirror_lower_kernel<<<grid, block, 0, st>>>(Kinv, ldi, N);
+    mirror_lower_kernel<<<grid, block, 0, st>>>(Kinv, ldi, N);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
@@ -322,15 +414,14 @@ extern "C" int gprb_lml_terms(const double *L, long long ldl, int N, const doubl
                               double *out_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(L && y && alpha && out_host && N > 0, "gprb_lml_terms: bad argument");
-    double *d = nullptr;
     { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
-    GPRB_CUDA(cudaMallocAsync((void **)&d, 2 * sizeof(double), st));
+    Scratch scratch(st);
+    double *d = (double *)scratch.get(2 * sizeof(double));
+    if (!d) return GPRB_ERR_CUDA;
     lml_terms_kernel<<<1, 1024, 0, st>>>(L, ldl, N, y, alpha, d);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
-    int rc = copy_scalars(out_host, d, 2, st);
-    cudaFreeAsync(d, st);
-    return rc;
+    return copy_scalars(out_host, d, 2, st);
 }
 
 extern "C" int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha, const double *Kinv, long long ldi,
@@ -340,19 +431,13 @@ extern "C" int gprb_lml_grad_trace(int N, int r0, int r1, const double *alpha, c
     GPRB_REQUIRE(alpha && Kinv && out_host && 0 <= r0 && r0 <= r1 && r1 <= N, "gprb_lml_grad_trace: bad argument");
     out_host[0] = out_host[1] = 0.0;
     if (r0 == r1) return GPRB_OK;
-    const int blocks = (r1 - r0) < 1184 ? (r1 - r0) : 1184;   // 8 x 148
-    double *d = nullptr;
     { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
-    GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
-    trace_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, alpha, Kinv, ldi, dK_rows, lddk, NE, we, wf, upper_only, d);
-    GPRB_LAUNCHED();
-    GPRB_CUDA(cudaGetLastError());
-    final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, d + 2 * blocks);
-    GPRB_LAUNCHED();
-    GPRB_CUDA(cudaGetLastError());
-    int rc = copy_scalars(out_host, d + 2 * blocks, 2, st);
-    cudaFreeAsync(d, st);
-    return rc;
+    Scratch scratch(st);
+    double *d = (double *)scratch.get(3 * sizeof(double));
+    if (!d) return GPRB_ERR_CUDA;
+    int rc = trace_enqueue(N, r0, r1, alpha, Kinv, ldi, dK_rows, lddk, NE, we, wf, 0.0, 0.0, upper_only, nullptr, 0, d, 0, scratch, st);
+    if (rc) return rc;
+    return copy_scalars(out_host, d, 2, st);
 }
 
 extern "C" int gprb_lml_grad_trace_rows(int N, int r0, int r1, const double *alpha, const double *Kinv_rows, long long ldr,
@@ -364,27 +449,14 @@ extern "C" int gprb_lml_grad_trace_rows(int N, int r0, int r1, const double *alp
     GPRB_REQUIRE(KinvE || r1 <= NE || NE == 0 || c0 == 0, "gprb_lml_grad_trace_rows: force rows need the energy rows of the inverse");
     out_host[0] = out_host[1] = 0.0;
     if (r0 == r1) return GPRB_OK;
-    // the kernel indexes Kinv[i * ld + j] with global (i, j): shift the base so that (r0, c0) is element 0 of the slab
-    const double *virt = reinterpret_cast<const double *>(reinterpret_cast<uintptr_t>(Kinv_rows) -
-                                                          (uintptr_t)(((long long)r0 * ldr + c0) * (long long)sizeof(double)));
-    const int blocks = (r1 - r0) < 1184 ? (r1 - r0) : 1184;
-    double *d = nullptr;
     { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
-    GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
-    trace_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, alpha, virt, ldr, dK_rows, lddk, NE, we, wf, 2, d, KinvE, ldE);
-    GPRB_LAUNCHED();
-    GPRB_CUDA(cudaGetLastError());
-    final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, d + 2 * blocks);
-    GPRB_LAUNCHED();
-    GPRB_CUDA(cudaGetLastError());
-    int rc = copy_scalars(out_host, d + 2 * blocks, 2, st);
-    cudaFreeAsync(d, st);
-    return rc;
-}
-
-__global__ void unit_columns_kernel(double *B, long long ldb, int n_rows, int col0) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n_rows) B[(long long)k * ldb + col0 + k] = 1.0;
+    Scratch scratch(st);
+    double *d = (double *)scratch.get(3 * sizeof(double));
+    if (!d) return GPRB_ERR_CUDA;
+    int rc = trace_enqueue(N, r0, r1, alpha, virtual_base(Kinv_rows, ldr, r0, c0), ldr, dK_rows, lddk, NE, we, wf, 0.0, 0.0, 2,
+                           KinvE, ldE, d, 0, scratch, st);
+    if (rc) return rc;
+    return copy_scalars(out_host, d, 2, st);
 }
 
 extern "C" int gprb_chol_inverse_rows(const double *L, long long ldl, int N, int r0, int r1, int c0,
@@ -395,26 +467,7 @@ extern "C" int gprb_chol_inverse_rows(const double *L, long long ldl, int N, int
     if (r0 == r1) return GPRB_OK;
     int rc = handles(st);
     if (rc) return rc;
-    // K^-1[T, T] = (L_TT L_TT^T)^-1 for the trailing index set T = [c0, N) (L^-1 is triangular), so rows
-    // [r0, r1) of the inverse, restricted to the columns >= c0, are the solution of the trailing system with
-    // the unit vectors of those rows as right-hand sides (symmetric: row = column).
-    const int n = N - c0, nrhs = r1 - r0;
-    GPRB_CUDA(cudaMemset2DAsync(out, ldo * sizeof(double), 0, (size_t)n * sizeof(double), nrhs, st));
-    unit_columns_kernel<<<(nrhs + 255) / 256, 256, 0, st>>>(out, ldo, nrhs, r0 - c0);
-    GPRB_LAUNCHED();
-    GPRB_CUDA(cudaGetLastError());
-    // what potrs does, through the 64-bit cuBLAS interface (N^2 may exceed 2^31, e.g. the S4 configuration):
-    // column-major view, K_T = U^T U with U in the upper triangle of the factor's buffer;  U^T Y = E, then U X = Y
-    const double one = 1.0;
-    const double *U = L + (long long)c0 * ldl + c0;
-    cublasStatus_t b1 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(0), CUBLAS_DIAG_NON_UNIT,
-                                       (int64_t)n, (int64_t)nrhs, &one, U, (int64_t)ldl, out, (int64_t)ldo);
-    cublasStatus_t b2 = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(1), CUBLAS_DIAG_NON_UNIT,
-                                       (int64_t)n, (int64_t)nrhs, &one, U, (int64_t)ldl, out, (int64_t)ldo);
-    if (b1 != CUBLAS_STATUS_SUCCESS || b2 != CUBLAS_STATUS_SUCCESS) {
-        gprb_set_error("cublasDtrsm_64 (inverse rows) status %d / %d", (int)b1, (int)b2); return GPRB_ERR_CUDA;
-    }
-    return GPRB_OK;
+    return inverse_rows_enqueue(L, ldl, N, r0, r1, c0, out, ldo, st);
 }
 
 extern "C" int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const double *alpha, const double *Kinv,
@@ -424,21 +477,96 @@ extern "C" int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const dou
                  "gprb_w_block_sum: bad argument");
     out_host[0] = 0.0;
     if (r0 == r1 || c0 == c1) return GPRB_OK;
-    const int blocks = (r1 - r0) < 1184 ? (r1 - r0) : 1184;
-    double *d = nullptr;
     { int rc0 = gprb_pool_init(); if (rc0) return rc0; }
-    GPRB_CUDA(cudaMallocAsync((void **)&d, (size_t)(2 * blocks + 2) * sizeof(double), st));
-    block_sum_kernel<<<blocks, 256, 0, st>>>(N, r0, r1, c0, c1, alpha, Kinv, ldi, d);
+    Scratch scratch(st);
+    double *d = (double *)scratch.get(3 * sizeof(double));
+    if (!d) return GPRB_ERR_CUDA;
+    int rc = block_sum_enqueue(N, r0, r1, c0, c1, alpha, Kinv, ldi, d, 0, scratch, st);
+    if (rc) return rc;
+    return copy_scalars(out_host, d, 1, st);
+}
+
+// One likelihood evaluation after the covariance build, enqueued back to back with ONE host synchronisation at the end
+// (GP.log_marginal_likelihood, gaussianprocess.py:160-198): K += noise, Cholesky in place, alpha = K^-1 y, log-det and
+// y.alpha, and -- want_grad -- the traces of W = alpha alpha^T - K^-1 against the rows of dK/dl this rank holds, with
+// K^-1 taken block of rows by block of rows from trailing-block triangular solves (no explicit inverse).
+//   ranges_host: n_ranges (r0, r1) row ranges of the assembled matrix whose rows of dK are stacked in dK_rows (NULL: no
+//   dK term, e.g. the Dot kernel); rows < NE hold the K_ee part, force rows K_fe and the J >= I blocks of K_ff.
+//   out_host[8]: 0 log-det term sum(log L_ii), 1 y.alpha, 2 1/2 tr(W dK) over the held rows, 3 1/2 sum W_ii noise_i^2,
+//   4 1/2 sum W_ii 2 noise_i, 5 1/2 sum of W over the held energy rows x all energy columns (want_s0, Dot sigma0 term).
+extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const double *y, double noise_e, double noise_f,
+                             const double *dK_rows, long long lddk, int n_ranges, const int *ranges_host,
+                             int want_grad, int want_s0, int parts, double *alpha, double *out_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(K && y && alpha && out_host && N > 0 && NE >= 0 && NE <= N && ldk >= N, "gprb_lml_eval: bad argument");
+    GPRB_REQUIRE(n_ranges >= 0 && (n_ranges == 0 || ranges_host), "gprb_lml_eval: bad row ranges");
+    int rc = handles(st);
+    if (rc) return rc;
+    for (int k = 0; k < 8; k++) out_host[k] = 0.0;
+    Scratch scratch(st);
+    int *info = (int *)scratch.get(2 * sizeof(int));
+    double *acc = (double *)scratch.get(9 * sizeof(double));      // [0..1] lml terms, [2..4] traces, [5..7] sigma0 block sum
+    if (!info || !acc) return GPRB_ERR_CUDA;
+    GPRB_CUDA(cudaMemsetAsync(acc, 0, 9 * sizeof(double), st));
+    add_noise_kernel<<<(N + 255) / 256, 256, 0, st>>>(K, ldk, N, NE, noise_e * noise_e, noise_f * noise_f);
+    GPRB_LAUNCHED();
+    if ((rc = factor_enqueue(K, ldk, N, info, scratch, st))) return rc;
+    GPRB_CUDA(cudaMemcpyAsync(alpha, y, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if ((rc = solve_vec_enqueue(K, ldk, N, alpha, info + 1))) return rc;
+    lml_terms_kernel<<<1, 1024, 0, st>>>(K, ldk, N, y, alpha, acc);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
-    final_sum_kernel<<<1, 32, 0, st>>>(d, blocks, d + 2 * blocks);
-    GPRB_LAUNCHED();
-    GPRB_CUDA(cudaGetLastError());
-    double tmp[2];
-    int rc = copy_scalars(tmp, d + 2 * blocks, 2, st);
-    out_host[0] = tmp[0];
-    cudaFreeAsync(d, st);
-    return rc;
+    if (want_grad) {
+        if (parts < 1) parts = 16;
+        const double we = noise_e * noise_e, wf = noise_f * noise_f, we2 = 2.0 * noise_e, wf2 = 2.0 * noise_f;
+        double *Einv = nullptr;
+        if (NE) {
+            Einv = (double *)scratch.get((size_t)NE * N * sizeof(double));
+            if (!Einv) return GPRB_ERR_CUDA;
+            if ((rc = inverse_rows_enqueue(K, ldk, N, 0, NE, 0, Einv, N, st))) return rc;
+        }
+        const int blk = std::max(512, (N + parts - 1) / parts);
+        long long off = 0;                                   // first row of the range inside dK_rows
+        for (int q = 0; q < n_ranges; q++) {
+            const int R0 = ranges_host[2 * q], R1 = ranges_host[2 * q + 1];
+            GPRB_REQUIRE(0 <= R0 && R0 <= R1 && R1 <= N, "gprb_lml_eval: bad row range [%d, %d)", R0, R1);
+            int a = R0;
+            while (a < R1) {
+                int b;
+                const double *rows; long long ldr; int c0;
+                void *slab = nullptr;
+                if (a < NE) {                                 // energy rows: a slice of K^-1[0:NE, :]
+                    b = std::min(R1, NE);
+                    rows = Einv + (size_t)a * N; ldr = N; c0 = 0;
+                } else {
+                    b = std::min(R1, a + blk);
+                    c0 = a; ldr = N - c0;
+                    GPRB_CUDA(cudaMallocAsync(&slab, (size_t)(b - a) * ldr * sizeof(double), st));
+                    rc = inverse_rows_enqueue(K, ldk, N, a, b, c0, (double *)slab, ldr, st);
+                    if (rc) { gprb_pool_free(slab, st); return rc; }
+                    rows = (const double *)slab;
+                }
+                const double *dptr = dK_rows ? dK_rows + (off + (a - R0)) * lddk : nullptr;
+                rc = trace_enqueue(N, a, b, alpha, virtual_base(rows, ldr, a, c0), ldr, dptr, lddk, NE, we, wf, we2, wf2, 2,
+                                   Einv, N, acc + 2, 1, scratch, st);
+                if (!rc && want_s0 && b <= NE)
+                    rc = block_sum_enqueue(N, a, b, 0, NE, alpha, Einv, N, acc + 5, 1, scratch, st);
+                gprb_pool_free(slab, st);                     // stream-ordered: released after the trace has read it
+                if (rc) return rc;
+                a = b;
+            }
+            off += R1 - R0;
+        }
+    }
+    double hacc[9];
+    int hinfo[2] = {-1, -1};
+    GPRB_CUDA(cudaMemcpyAsync(hacc, acc, sizeof hacc, cudaMemcpyDeviceToHost, st));
+    GPRB_CUDA(cudaMemcpyAsync(hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost, st));
+    GPRB_CUDA(cudaStreamSynchronize(st));
+    if (hinfo[0] != 0) { gprb_set_error("matrix not positive definite (potrf info = %d)", hinfo[0]); return GPRB_ERR_LINALG; }
+    out_host[0] = hacc[0]; out_host[1] = hacc[1]; out_host[2] = hacc[2]; out_host[3] = hacc[3]; out_host[4] = hacc[4];
+    out_host[5] = hacc[5];
+    return GPRB_OK;
 }
 
 extern "C" int gprb_predict(int m, int N, const double *Ks, long long ldks, const double *alpha,
@@ -495,7 +623,7 @@ extern "C" int gprb_predict_chol(int m, int N, const double *Ks, long long ldks,
     GPRB_CUDA(cudaMemcpy2DAsync(work, (size_t)N * sizeof(double), Ks, (size_t)ldks * sizeof(double), (size_t)N * sizeof(double), m,
                                 cudaMemcpyDeviceToDevice, st));
     const double one = 1.0;
-    cublasStatus_t bs = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, factor_uplo(), solve_op(0), CUBLAS_DIAG_NON_UNIT,
+    cublasStatus_t bs = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, FACTOR_UPLO, solve_op(0), CUBLAS_DIAG_NON_UNIT,
                                        (int64_t)N, (int64_t)m, &one, L, (int64_t)ldl, work, (int64_t)N);
     if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDtrsm_64 (predict) status %d", (int)bs); return GPRB_ERR_CUDA; }
     predict_rows_chol_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, work, diag, mean, var);

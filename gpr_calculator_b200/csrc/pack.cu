@@ -135,6 +135,14 @@ void gprb_pool_free(void *ptr, cudaStream_t st) {
     if (cudaFreeAsync(ptr, st) != cudaSuccess) { cudaGetLastError(); cudaFree(ptr); }
 }
 
+int gprb_check_device(const gprb_pack *p, const char *who) {
+    int dev = -1;
+    GPRB_CUDA(cudaGetDevice(&dev));
+    GPRB_REQUIRE(p == nullptr || p->device == dev, "%s: the pack was created on device %d but the current device is %d", who,
+                 p ? p->device : -1, dev);
+    return GPRB_OK;
+}
+
 extern "C" void gprb_pack_destroy(gprb_pack *p) {
     if (!p) return;
     cudaStream_t st = p->stream;

@@ -124,6 +124,16 @@ def all_gather_floats(value, device="cpu", group=None):
     return [float(v) for v in t.cpu()]
 
 
+def broadcast_floats(values, src=0, device="cpu", group=None):
+    """Every rank returns rank `src`'s list of python floats."""
+    rank, size = world()
+    if size == 1:
+        return [float(v) for v in values]
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    dist.broadcast(t, src=src if group is None else dist.get_global_rank(group, src), group=group)
+    return [float(v) for v in t.cpu()]
+
+
 def all_reduce_sum(values, device="cpu", group=None):
     """Sum a small list of python floats over ranks."""
     rank, size = world()

@@ -18,6 +18,7 @@ Persistence (:632-821): the json model file plus an ASE sqlite database of the l
 read and written by gpr_calculator_b200.asedb (ASE's file layout, no ASE needed); GP.load recomputes
 the descriptors in batches on the device.
 """
+import ctypes
 import json
 import logging
 import os
@@ -48,9 +49,6 @@ def _zero_build_targets(K, NE, chunks=16):
     per = 3 * max(1, -(-((N - NE) // 3) // chunks))
     for r in range(NE, N, per):
         K[r:r + per, r:].zero_()
-
-
-_FACTOR_LOWER = os.environ.get("GPRB_POTRF_LOWER") is not None      # read once, like the library does
 
 
 def _row_pieces(r_ranges, NE, N, parts=16, min_rows=512):
@@ -164,15 +162,10 @@ class GP():
     def L_(self):
         if self._L_dev is None:
             return None
-        M = self._L_dev.cpu().numpy()
-        # the factor lives in the row-major lower triangle; with the experimental GPRB_POTRF_LOWER=1 (gp_linalg.cu) it is
-        # L^T in the upper one
-        return np.triu(M).T.copy() if _FACTOR_LOWER else np.tril(M)
+        return np.tril(self._L_dev.cpu().numpy())       # the factor lives in the row-major lower triangle
 
     @L_.setter
     def L_(self, v):
-        if v is not None and _FACTOR_LOWER:
-            v = np.asarray(v, dtype=np.float64).T
         self._L_dev = None if v is None else torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64), device="cuda").contiguous()
 
     @property
@@ -326,13 +319,7 @@ class GP():
 
     def _factor(self, K, noise_e, noise_f):
         """K += noise; in-place Cholesky; alpha = K^-1 y.  Returns alpha (device vector)."""
-        N = K.shape[0]
-        NE = self._n_energy_rows()
-        st = stream()
-        _lib.call("gprb_add_noise", ptr(K), N, N, NE, float(noise_e), float(noise_f), st)
-        _lib.call("gprb_chol_factor", ptr(K), N, N, st)
-        alpha = torch.as_tensor(self.y_train[:, 0], device="cuda").clone().contiguous()
-        _lib.call("gprb_chol_solve_vec", ptr(K), N, N, ptr(alpha), st)
+        alpha, _ = self._lml_eval(K, None, [], noise_e, noise_f, want_grad=False)
         return alpha
 
     def set_K_inv(self):
@@ -372,40 +359,83 @@ class GP():
         K, dK, r_ranges = self._build_K(grad=eval_gradient)
         N = K.shape[0]
         NE = self._n_energy_rows()
-        st = stream()
+        full_inverse = os.environ.get("GPRB_FULL_INVERSE", "0") not in ("", "0")
         try:
-            alpha = self._factor(K, noise_e, noise_f)
+            alpha, out = self._lml_eval(K, dK if is_rbf else None, r_ranges, noise_e, noise_f,
+                                        want_grad=eval_gradient and not full_inverse, want_s0=not is_rbf)
         except _lib.NotPositiveDefinite:
             return (-np.inf, np.zeros_like(params)) if eval_gradient else -np.inf
-
-        y = torch.as_tensor(self.y_train[:, 0], device="cuda")
-        terms = (ctypes_double * 2)()
-        _lib.call("gprb_lml_terms", ptr(K), N, N, ptr(y), ptr(alpha), terms, st)
-        logdet, ya = terms[0], terms[1]
+        logdet, ya = out[0], out[1]
         MLL = -0.5 * ya - logdet - N / 2 * np.log(2 * np.pi)
         if not eval_gradient:
-            return MLL
+            return self._sync_ranks(MLL)
+        if full_inverse:
+            g_l, half_w_noise, half_w_base, g_s0 = self._lml_gradient_full_inverse(K, alpha, dK, r_ranges, N, NE, noise_e,
+                                                                                    noise_f, is_rbf)
+        else:
+            g_l, half_w_noise, half_w_base, g_s0 = out[2], out[3], out[4], out[5]
+        if gdist.world()[1] > 1:
+            g_l, half_w_noise, half_w_base, g_s0 = gdist.all_reduce_sum([g_l, half_w_noise, half_w_base, g_s0], device="cuda")
+        if not is_rbf:
+            # Dot: dK/dsigma0 = 0.8 * 2 sigma^2 sigma0 on the E-E block only (dot_kernel.py:58)
+            g_s0 *= 0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0
+        # 1/2 tr(W (2/sigma) K0), K0 = K - noise:  tr(W K) = y.alpha - N
+        g_sigma = ((ya - N) - 2.0 * half_w_noise) / kernel.sigma
+        llg = np.array([g_sigma, g_l if is_rbf else g_s0, half_w_base])
+        if self.noise_bounds is None:
+            llg = llg[:-1]
+        return self._sync_ranks(MLL, llg)
 
+    def _sync_ranks(self, lml, grad=None):
+        """Every rank continues with rank 0's values (the reference broadcasts the parameters after each optimiser
+        step, gaussianprocess.py:246-247, 305-306): the ranks' copies of K may differ in the last bit (summation order
+        of row groups that straddle CTAs), and the host optimiser must take the same decisions on every rank or
+        the ranks would issue different numbers of collective builds."""
+        if gdist.world()[1] == 1:
+            return lml if grad is None else (lml, grad)
+        vals = gdist.broadcast_floats([lml] + ([] if grad is None else [float(g) for g in grad]), src=0, device="cuda")
+        return vals[0] if grad is None else (vals[0], np.array(vals[1:]))
+
+    def _lml_eval(self, K, dK, r_ranges, noise_e, noise_f, want_grad, want_s0=False):
+        """gprb_lml_eval on the built covariance: noise, in-place Cholesky, alpha and the likelihood scalars with one
+        host synchronisation (gaussianprocess.py:160-198 without the explicit inverse of :195).
+
+        W = alpha alpha^T - K^-1 and dK/dl are symmetric, so tr(W dK) needs K^-1 only on and right of the
+        diagonal, for the rows of dK this rank holds.  For a block of rows [r0, r1) that is K^-1[r0:r1, r0:N], a solve
+        with the TRAILING block of the factor only (K^-1[T,T] = (L_TT L_TT^T)^-1), plus K^-1[0:NE, :] for the energy
+        columns: the same 2 N^3 / 3 flops as potri but as large triangular solves, no N x N inverse buffer, and on G
+        GPUs every rank solves only for its own rows.  Returns (alpha, the 8 scalars of gprb_lml_eval)."""
+        N = K.shape[0]
+        NE = self._n_energy_rows()
+        y = torch.as_tensor(self.y_train[:, 0], device="cuda").contiguous()
+        alpha = torch.empty(N, dtype=F64, device="cuda")
+        out = (ctypes_double * 8)()
+        flat = [int(v) for r in r_ranges for v in r]
+        ranges = (ctypes.c_int * max(len(flat), 1))(*flat)
+        _lib.call("gprb_lml_eval", ptr(K), K.stride(0), N, NE, ptr(y), float(noise_e), float(noise_f),
+                  ptr(dK), dK.stride(0) if dK is not None else N, len(r_ranges), ranges, int(bool(want_grad)),
+                  int(bool(want_s0)), int(os.environ.get("GPRB_INVERSE_ROW_PARTS", "16")), ptr(alpha), out, stream())
+        return alpha, [float(v) for v in out]
+
+    def _lml_gradient_full_inverse(self, K, alpha, dK, r_ranges, N, NE, noise_e, noise_f, is_rbf):
+        """The reference's literal route (gaussianprocess.py:195): the explicit inverse on every rank (cuSOLVER potri),
+        kept behind GPRB_FULL_INVERSE=1 as the cross-check of the inverse-rows route."""
+        st = stream()
         out = (ctypes_double * 2)()
         sharded = gdist.world()[1] > 1
-        if os.environ.get("GPRB_FULL_INVERSE", "0") in ("", "0"):
-            return self._lml_gradient_rows(K, alpha, dK, r_ranges, N, NE, ya, MLL, noise_e, noise_f, is_rbf)
-        # reference route (gaussianprocess.py:195): the explicit inverse on every rank (cuSOLVER potri)
         Kinv = torch.empty((N, N), dtype=F64, device="cuda")
         _lib.call("gprb_chol_inverse", ptr(K), N, N, ptr(Kinv), N, st)
         # 1/2 tr(W dK/dl) over the rows of dK held by this rank (W, dK symmetric: columns j >= i,
         # off-diagonal terms doubled -- the blocks left of the diagonal are not built when sharded)
         # + 1/2 sum_i W_ii noise_i^2 (for the sigma term)
-        g_l = 0.0
-        half_w_noise = 0.0
-        half_w_base = 0.0
+        g_l = half_w_noise = half_w_base = g_s0 = 0.0
         off = 0
         for (r0, r1) in r_ranges:
             if r1 > r0:
                 dptr = c_vp(0)
                 if is_rbf:
                     dptr = c_vp(dK.data_ptr() + off * dK.stride(0) * 8)
-                _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, dptr, N, NE,
+                _lib.call("gprb_lml_grad_trace", N, r0, r1, ptr(alpha), ptr(Kinv), N, dptr, dK.stride(0) if is_rbf else N, NE,
                           float(noise_e) ** 2, float(noise_f) ** 2, 2 if sharded else 1, out, st)
                 g_l += out[0]
                 half_w_noise += out[1]
@@ -413,71 +443,13 @@ class GP():
                           2.0 * float(noise_e), 2.0 * float(noise_f), 1, out, st)
                 half_w_base += out[1]
             off += r1 - r0
-        g_s0 = 0.0
         if not is_rbf:
-            # Dot: dK/dsigma0 = 0.8 * 2 sigma^2 sigma0 on the E-E block only (dot_kernel.py:58)
             (r0, r1) = r_ranges[0]
             r1 = min(r1, NE)            # energy rows held by this rank (the first range starts with them)
             if r1 > r0 and NE > 0:
                 _lib.call("gprb_w_block_sum", N, r0, r1, 0, NE, ptr(alpha), ptr(Kinv), N, out, st)
-                g_s0 = out[0] * (0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0)
-        if sharded:
-            g_l, half_w_noise, half_w_base, g_s0 = gdist.all_reduce_sum([g_l, half_w_noise, half_w_base, g_s0], device="cuda")
-        # 1/2 tr(W (2/sigma) K0), K0 = K - noise:  tr(W K) = y.alpha - N
-        g_sigma = ((ya - N) - 2.0 * half_w_noise) / kernel.sigma
-        llg = np.array([g_sigma, g_l if is_rbf else g_s0, half_w_base])
-        if self.noise_bounds is None:
-            llg = llg[:-1]
-        return MLL, llg
-
-    def _lml_gradient_rows(self, L, alpha, dK, r_ranges, N, NE, ya, MLL, noise_e, noise_f, is_rbf):
-        """Gradient of the LML (gaussianprocess.py:188-198) without the explicit inverse of :195.
-
-        W = alpha alpha^T - K^-1 and dK/dl are symmetric, so tr(W dK) needs K^-1 only on and right of the
-        diagonal, for the rows of dK this rank holds (all rows on one GPU; its energy rows with their K_ee part and
-        its force rows with K_fe and the J >= I blocks of K_ff when row-sharded).  For a block of rows [r0, r1) that
-        is K^-1[r0:r1, r0:N], a solve with the TRAILING block of the factor only (K^-1[T,T] = (L_TT L_TT^T)^-1,
-        gprb_chol_inverse_rows), plus K^-1[0:NE, :] for the energy columns.  Walking the rows in blocks costs the
-        same 2 N^3 / 3 flops as potri but as large triangular solves (about twice potri's rate on B200), needs
-        no N x N inverse buffer, and on G GPUs every rank solves only for its own rows (about 1/G of the work,
-        no communication); the resulting scalars are all-reduced."""
-        st = stream()
-        out = (ctypes_double * 2)()
-        kernel = self.kernel
-        Einv = None
-        if NE:
-            Einv = torch.empty((NE, N), dtype=F64, device="cuda")
-            _lib.call("gprb_chol_inverse_rows", ptr(L), N, N, 0, NE, 0, ptr(Einv), N, st)
-        g_l = half_w_noise = half_w_base = g_s0 = 0.0
-        for (r0, r1, doff) in _row_pieces(r_ranges, NE, N, parts=int(os.environ.get("GPRB_INVERSE_ROW_PARTS", "16"))):
-            if r1 <= NE:
-                rows, ldr, c0 = Einv[r0:r1], N, 0                 # energy rows: a slice of K^-1[0:NE, :]
-            else:
-                c0 = r0
-                rows = torch.empty((r1 - r0, N - c0), dtype=F64, device="cuda")
-                ldr = N - c0
-                _lib.call("gprb_chol_inverse_rows", ptr(L), N, N, r0, r1, c0, ptr(rows), ldr, st)
-            dptr = c_vp(dK.data_ptr() + doff * dK.stride(0) * 8) if is_rbf else c_vp(0)
-            ldd = dK.stride(0) if is_rbf else N
-            _lib.call("gprb_lml_grad_trace_rows", N, r0, r1, ptr(alpha), ptr(rows), ldr, c0, ptr(Einv), N, dptr, ldd, NE,
-                      float(noise_e) ** 2, float(noise_f) ** 2, out, st)
-            g_l += out[0]
-            half_w_noise += out[1]
-            _lib.call("gprb_lml_grad_trace_rows", N, r0, r1, ptr(alpha), ptr(rows), ldr, c0, ptr(Einv), N, c_vp(0), N, NE,
-                      2.0 * float(noise_e), 2.0 * float(noise_f), out, st)
-            half_w_base += out[1]
-            if not is_rbf and r1 <= NE:
-                # Dot: dK/dsigma0 = 0.8 * 2 sigma^2 sigma0 on the E-E block only (dot_kernel.py:58)
-                _lib.call("gprb_w_block_sum", N, r0, r1, 0, NE, ptr(alpha), ptr(Einv), N, out, st)
-                g_s0 += out[0] * (0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0)
-            del rows
-        if gdist.world()[1] > 1:
-            g_l, half_w_noise, half_w_base, g_s0 = gdist.all_reduce_sum([g_l, half_w_noise, half_w_base, g_s0], device="cuda")
-        g_sigma = ((ya - N) - 2.0 * half_w_noise) / kernel.sigma
-        llg = np.array([g_sigma, g_l if is_rbf else g_s0, half_w_base])
-        if self.noise_bounds is None:
-            llg = llg[:-1]
-        return MLL, llg
+                g_s0 = out[0]
+        return g_l, half_w_noise, half_w_base, g_s0
 
     def optimize(self, fun, theta0, bounds, maxiter=10):
         """L-BFGS-B on the host, identical options to gaussianprocess.py:215-219."""
@@ -528,6 +500,8 @@ class GP():
             if self.rank == 0:
                 print(f"Update GP model => {self.N_queue}/{maxiter}")
             params, _ = self.optimize(obj_func, hyper_params, hyper_bounds, maxiter=maxiter)
+            if gdist.world()[1] > 1:       # params = comm.bcast(params, root=0), gaussianprocess.py:305-306
+                params = np.array(gdist.broadcast_floats(params, src=0, device="cuda"))
             if self.noise_bounds is not None:
                 self.kernel.update(params[:-1])
                 self.noise_e = params[-1]
@@ -1160,8 +1134,6 @@ class GP():
         instance.noise_bounds = dict0["noise"]["bounds"]
         return instance
 
-
-import ctypes  # noqa: E402
 
 ctypes_double = ctypes.c_double
 

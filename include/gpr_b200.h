@@ -186,6 +186,22 @@ int gprb_fp64_dmma_peak(double *tflops_host, void *stream);
 /* 1/2 sum over the block [r0,r1) x [c0,c1) of (alpha_i alpha_j - Kinv_ij)   (Dot d/dsigma0 term) */
 int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const double *alpha_dev, const double *Kinv_dev,
                      long long ldi, double *out_host, void *stream);
+/* One likelihood evaluation after the covariance build, enqueued back to back with a single host synchronisation
+ * (GP.log_marginal_likelihood, gaussianprocess.py:160-198; the scipy cholesky / cho_solve / einsum steps of :174-198):
+ * K += noise on the diagonal, in-place Cholesky, alpha = K^-1 y, and -- want_grad -- the traces of
+ * W = alpha alpha^T - K^-1 against the rows of dK/dl this rank holds, K^-1 taken block of rows by block of rows
+ * (N / parts rows, >= 512) from trailing-block triangular solves as in gprb_chol_inverse_rows (no explicit inverse).
+ *   ranges_host[2 n_ranges]: row ranges (r0, r1) of the assembled matrix whose rows of dK are stacked in
+ *     dK_rows_dev (leading dimension lddk; NULL = no dK term); rows < NE carry the K_ee part, force rows K_fe and
+ *     the J >= I blocks of K_ff (the layout of gprb_lml_grad_trace with upper_only = 2; a full dK satisfies it).
+ *   alpha_dev[N] receives alpha; K_dev holds the factor on return.
+ *   out_host[8]: [0] sum_i log L_ii, [1] y.alpha, [2] 1/2 tr(W dK) over the held rows, [3] 1/2 sum W_ii noise_i^2,
+ *     [4] 1/2 sum W_ii 2 noise_i, [5] 1/2 sum of W over (held energy rows) x (all energy columns) when want_s0
+ *     (the Dot kernel's d/dsigma0 term, dot_kernel.py:58).  Sharded callers all-reduce [2..5].
+ * Returns GPRB_ERR_LINALG when K is not positive definite (gaussianprocess.py:174-177). */
+int gprb_lml_eval(double *K_dev, long long ldk, int N, int NE, const double *y_dev, double noise_e, double noise_f,
+                  const double *dK_rows_dev, long long lddk, int n_ranges, const int *ranges_host,
+                  int want_grad, int want_s0, int parts, double *alpha_dev, double *out_host, void *stream);
 /* mean[i] = Ks[i,:].alpha ;  if var_dev: var[i] = max(diag[i] - Ks[i,:] Kinv Ks[i,:]^T, 0)
  * (cuBLAS DGEMM + fused row reduction; gaussianprocess.py:880, 904-908).  work_dev: [m, N] scratch. */
 int gprb_predict(int m, int N, const double *Ks_dev, long long ldks, const double *alpha_dev,
