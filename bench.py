@@ -148,10 +148,13 @@ def reference_build(e_items, f_items, threads):
         ff = list(pool.map(lambda c: O.kff_C(ok.list_to_tuple(c), F, SIGMA, ELL, ZETA, grad=True), chunks(f_items)))
         fe = list(pool.map(lambda c: O.kef_C(E, ok.list_to_tuple(c), SIGMA, ELL, ZETA, grad=True), chunks(f_items)))
         ee = list(pool.map(lambda c: O.kee_C(ok.list_to_tuple(c, mode="energy"), E, SIGMA, ELL, ZETA, grad=True), chunks(e_items)))
-    Kff = np.vstack([b[0] for b in ff])
-    Kef = np.hstack([b[0] for b in fe])
-    Kee = np.vstack([b[0] for b in ee])
-    return np.block([[Kee, Kef], [Kef.T, Kff]])
+    out = []
+    for k in (0, 2):          # K and dK/dl (the wrappers return (K, dK/dsigma, dK/dl))
+        Kff = np.vstack([b[k] for b in ff])
+        Kef = np.hstack([b[k] for b in fe])
+        Kee = np.vstack([b[k] for b in ee])
+        out.append(np.block([[Kee, Kef], [Kef.T, Kff]]))
+    return out[0], out[1]
 
 
 def sample_pairs(e_items, f_items):
@@ -165,16 +168,265 @@ def run_cpu(n_struct, nrep, seed0, steps, warmup, threads):
     ok.build(ref=os.path.isdir("/root/reference"), port=True)
     e_items, f_items = cpu_sample(n_struct, nrep, seed0)
     fl = flops_of(*sample_pairs(e_items, f_items))
+    last = None
     for _ in range(warmup):
         reference_build(e_items, f_items, threads)
     t0 = time.perf_counter()
     for _ in range(steps):
-        reference_build(e_items, f_items, threads)
+        last = reference_build(e_items, f_items, threads)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     kind = "reference" if ok.have_ref() else "port"
     sample = ("first %d structures of the workload (%d E + %d F centres, %.3g K_ff pairs), K and dK/dl "
               "(rbf_k*_many_with_grad)" % (n_struct, len(e_items), len(f_items), sample_pairs(e_items, f_items)[0]))
-    return fl / dt * 1e-9, dt, kind, sample
+    return fl / dt * 1e-9, dt, kind, sample, (e_items, f_items, last)
+
+
+PARITY_TOL = 1e-10
+
+
+def parity_vs_reference(e_items, f_items, K_ref, dK_ref, atoms_list):
+    """The CUDA path on the SAME host descriptors as the CPU leg (real Cu32 rows: cos-similarity 0.998..1, |x| ~ 7e3,
+    l = 0.1) against the K / dK/dl the reference C++ just produced (rbf_kernel.cpp:5-98, 101-253, 475-640).
+    Two measures per matrix: per entry against the Cauchy-Schwarz scale sqrt(K_ii K_jj) of that entry (for dK/dl times
+    the bound (1/l^3 + 2/l) of |dlog k/dl|), and against the largest entry of its block (EE, EF, FF)."""
+    import torch
+    from gpr_calculator_b200.kernels import RBF_mb
+    from gpr_calculator_b200.utilities import list_to_tuple
+    data = {"energy": list_to_tuple(e_items, mode="energy"), "force": list_to_tuple(f_items)}
+    K, dK = RBF_mb(para=[SIGMA, ELL], zeta=ZETA).k_total_device(data, None, grad=True)
+    K, dK = K.cpu().numpy(), dK.cpu().numpy()
+    NE = len(e_items)
+    d = np.sqrt(np.abs(np.diag(K_ref)))
+    cs = np.outer(d, d)
+    out = {"max_rel_K": float((np.abs(K - K_ref) / cs).max()),
+           "max_rel_dK": float((np.abs(dK - dK_ref) / (cs * (1.0 / ELL ** 3 + 2.0 / ELL))).max())}
+    blocks = {"ee": (slice(0, NE), slice(0, NE)), "ef": (slice(0, NE), slice(NE, None)), "ff": (slice(NE, None), slice(NE, None))}
+    for name, (r, c) in blocks.items():
+        out["block_rel_K_" + name] = float(np.abs(K[r, c] - K_ref[r, c]).max() / np.abs(K_ref[r, c]).max())
+        out["block_rel_dK_" + name] = float(np.abs(dK[r, c] - dK_ref[r, c]).max() / np.abs(dK_ref[r, c]).max())
+    # descriptor producer on the same structures: device SO3 against the numpy restatement the CPU leg used
+    from gpr_calculator_b200.SO3 import SO3
+    r = SO3(nmax=3, lmax=4, rcut=5.0).calculate_batch(atoms_list, to_host=False)
+    x_dev = r["x"].cpu().numpy()
+    x_ref = np.concatenate([x for x, _ in e_items])
+    out["so3_max_rel_x"] = float(np.abs(x_dev - x_ref).max() / np.abs(x_ref).max())
+    out.update({"n": int(K_ref.shape[0]), "tol": PARITY_TOL,
+                "reference": "oracle/_ref (unmodified rbf_kernel.cpp) on the first %d structures, same host descriptors" % len(e_items)})
+    worst = max(v for k, v in out.items() if k.startswith(("max_rel", "block_rel")))
+    out["passed"] = bool(worst <= PARITY_TOL)
+    return out
+
+
+def sharded_parity(des, nrep, seed0, n_struct=24):
+    """Multi-GPU parity before anything is timed: the row-sharded build (fused peer gather or NCCL gather) of a small
+    workload against the window-free build of the same packs on this rank; LML and gradient against an unsharded
+    evaluation of the same algebra (every rank evaluates; the caller reduces with MAX)."""
+    import torch
+    from gpr_calculator_b200 import device as gdev, dist as gdist, synthetic as syn
+    from gpr_calculator_b200.gaussianprocess import GP
+    from gpr_calculator_b200.kernels import RBF_mb
+    labelled = syn.structures(n_struct, nrep, seed0)
+    E_dev, F_dev = syn.packed_from_batch(des, [a for a, _, _ in labelled])
+    e = gdev.Pack(E_dev[0], E_dev[1], E_dev[2])
+    f = gdev.Pack(F_dev[0], F_dev[2], F_dev[3], dxdr=F_dev[1])
+    gp = GP(kernel=RBF_mb(para=[SIGMA, ELL], zeta=ZETA), descriptor=des, noise_e=NOISE_E, noise_f=NOISE_F, log_file=None)
+    gp.train_x = {"energy": e, "force": f}
+    gp.y_train = syn.targets(labelled)
+    K1, dK1 = gp.kernel.k_total_device(gp.train_x, None, grad=True)
+    NE, N = e.n_groups, K1.shape[0]
+    errK = errdK = 0.0
+    for _ in range(2):                        # the second build re-uses (and re-zeroes) the peer-mapped matrix
+        K, dK, ranges = gp._build_K(grad=True)
+        errK = max(errK, float((K - K1).abs().max() / K1.abs().max()))
+        off = 0
+        cols = torch.arange(N, device="cuda")
+        for (r0, r1) in ranges:
+            if r1 > r0:
+                rows, ref = dK[off:off + (r1 - r0)], dK1[r0:r1]
+                rr = torch.arange(r0, r1, device="cuda")
+                if r1 <= NE:
+                    mask = (cols[None, :] < NE).expand(r1 - r0, N)
+                else:
+                    mask = (cols[None, :] < NE) | (((cols[None, :] - NE) // 3) >= ((rr[:, None] - NE) // 3))
+                errdK = max(errdK, float(((rows - ref).abs() * mask).max() / dK1.abs().max()))
+            off += r1 - r0
+    theta = np.array([SIGMA, ELL])
+    lml, grad = gp.log_marginal_likelihood(theta, eval_gradient=True)
+    # the same evaluation without sharding: this rank's window-free K / dK through the same entry point
+    alpha, out = gp._lml_eval(K1.clone(), dK1, [(0, N)], NOISE_E, NOISE_F, want_grad=True)
+    lml1 = -0.5 * out[1] - out[0] - N / 2 * np.log(2 * np.pi)
+    g1 = np.array([((out[1] - N) - 2.0 * out[3]) / SIGMA, out[2]])
+    gp.release_peer()
+    return {"max_rel_K": errK, "max_rel_dK": errdK, "lml_rel": abs(lml - lml1) / abs(lml1),
+            "grad_rel": float(np.abs(grad - g1).max() / np.abs(g1).max()), "N": int(N),
+            "gather": "peer" if gdist.peer_gather_enabled() else "nccl"}
+
+
+def _median_ms(fn, reps):
+    import torch
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    return float(np.median(ts))
+
+
+def small_n_block(des):
+    """Per-step retrain latency at the sizes of BASELINE configs 1-3 (on-the-fly runs: N = 50 ... 770).
+    c1a / c1b: Cu32 synthetic sets (2 E + 16 F centres = 50 rows, 4 E + 56 F = 172 rows); c2: the reference's real
+    Pd4/MgO training set (tests/golden/pd4.npz = examples/database/pd4-RBF.db: 155 E x 220 atoms, three species, + 205 F
+    centres = 770 rows, 34 100 stacked energy rows) with its stored hyper-parameters."""
+    import contextlib
+    import io
+    import tempfile
+    import torch
+    from gpr_calculator_b200 import _lib, asedb, synthetic as syn
+    from gpr_calculator_b200.gaussianprocess import GP
+    from gpr_calculator_b200.kernels import RBF_mb
+    from gpr_calculator_b200.utilities import SimpleAtoms
+    out = {}
+
+    def measure(gp, theta, probe_atoms, tag, what):
+        lml = lambda: gp.log_marginal_likelihood(theta, eval_gradient=True)     # noqa: E731
+        lml()
+        lml()
+        ms_lml = _median_ms(lml, 15)
+        _lib.PROFILE = []
+        lml()
+        torch.cuda.synchronize()
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        parts = {}
+        for n, a, b, h in prof:
+            parts[n] = round(parts.get(n, 0.0) + a.elapsed_time(b), 4)
+        with contextlib.redirect_stdout(io.StringIO()):
+            gp.kernel.update(list(theta))
+            gp.fit(opt=True, show=False, maxiter=10)
+            gp.kernel.update(list(theta))
+            t0 = time.perf_counter()
+            gp.fit(opt=True, show=False, maxiter=10)
+            torch.cuda.synchronize()
+            ms_fit = (time.perf_counter() - t0) * 1e3
+        pred = lambda: gp.predict_structure(probe_atoms, stress=False, return_std=True)   # noqa: E731
+        pred()
+        pred()
+        ms_pred = _median_ms(pred, 15)
+        out[tag] = {"workload": what, "N": int(len(gp.y_train)), "lml_grad_ms": ms_lml, "fit_maxiter10_ms": ms_fit,
+                    "predict_structure_ms": ms_pred, "lml_device_ms_by_entry_point": parts}
+
+    for tag, n_s, centres in (("c1_n50", 2, 8), ("c1_n172", 4, 14)):
+        labelled = syn.structures(n_s, 2, 2000)
+        E_dev, F_dev = syn.packed_from_batch(des, [a for a, _, _ in labelled], centres_per_structure=centres)
+        E_h, _k1 = syn.to_host(E_dev)
+        F_h, _k2 = syn.to_host(F_dev)
+        gp = GP(kernel=RBF_mb(para=[SIGMA, ELL], zeta=ZETA), descriptor=des, noise_e=NOISE_E, noise_f=NOISE_F, log_file=None)
+        gp.train_x = {"energy": E_h, "force": F_h}
+        gp.y_train = syn.targets(labelled, centres_per_structure=centres)
+        gp.N_energy, gp.N_forces = n_s, n_s * centres
+        measure(gp, np.array([SIGMA, ELL]), syn.cu_fcc(2, 5000)[0], tag,
+                "%d Cu32 structures: %d E + %d F centres" % (n_s, n_s, n_s * centres))
+    path = os.path.join(ROOT, "tests", "golden", "pd4.npz")
+    if os.path.exists(path):
+        g = np.load(path)
+        with tempfile.TemporaryDirectory() as tmp:
+            rows = []
+            for k in range(len(g["energy"])):
+                at = SimpleAtoms(g["numbers"], g["positions"][k], g["cell"], g["pbc"])
+                f_in = g["force_in"][g["force_in_ptr"][k]:g["force_in_ptr"][k + 1]]
+                rows.append((at, {"dft_energy": float(g["dft_energy"][k]), "dft_fmax": float(np.abs(g["force"][k]).max())},
+                             {"energy": float(g["energy"][k]), "force": g["force"][k], "energy_in": bool(g["energy_in"][k]),
+                              "force_in": [int(i) for i in f_in]}))
+            db, js = os.path.join(tmp, "pd4.db"), os.path.join(tmp, "pd4.json")
+            asedb.write_rows(db, rows)
+            model = json.loads(str(g["model_json"]))
+            model["db_filename"] = db
+            with open(js, "w") as fp:
+                json.dump(model, fp)
+            with contextlib.redirect_stdout(io.StringIO()):
+                gp = GP.load(js)
+        gp.log_file = None
+        theta = np.array(gp.kernel.parameters())
+        measure(gp, theta, SimpleAtoms(g["numbers"], g["positions"][-1], g["cell"], g["pbc"]), "c2_pd4",
+                "Pd4/MgO fixture of the reference (examples/database/pd4-RBF.db): 155 E x 220 atoms (Mg/O/Pd) + 205 F centres")
+        e_rows = int(gp.train_x["energy"][0].shape[0])
+        kee_ms = out["c2_pd4"]["lml_device_ms_by_entry_point"].get("gprb_kee", 0.0)
+        if kee_ms > 0:
+            pairs = sum(int((gp.train_x["energy"][1] == z).sum()) ** 2 for z in np.unique(gp.train_x["energy"][1]))
+            out["c2_pd4"]["kee"] = {"energy_rows": e_rows, "same_species_pairs": pairs, "ms": kee_ms,
+                                    "tflops": 2.0 * gp.train_x["energy"][0].shape[1] * pairs / kee_ms * 1e-9,
+                                    "flop_per_pair": "2 d (K_ee with dK/dl, rbf_kernel.cpp:5-98)"}
+    return out
+
+
+def s4_block(des, maxiter, budget_s):
+    """BASELINE config 4: 200 x Cu fcc 108 atoms (N = 65 000): one K + dK/dl build and one GP.fit(opt=True, maxiter)."""
+    import contextlib
+    import io
+    import torch
+    from gpr_calculator_b200 import _lib, device as gdev, synthetic as syn
+    from gpr_calculator_b200.gaussianprocess import GP
+    from gpr_calculator_b200.kernels import RBF_mb
+    n_struct, nrep, seed0, desc = WORKLOADS["s4"]
+    labelled = syn.structures(n_struct, nrep, seed0)
+    E_dev, F_dev = syn.packed_from_batch(des, [a for a, _, _ in labelled], chunk=16)
+    e_pack = gdev.Pack(E_dev[0], E_dev[1], E_dev[2])
+    f_pack = gdev.Pack(F_dev[0], F_dev[2], F_dev[3], dxdr=F_dev[1])
+    p_ff = syn.pair_counts(F_dev[2].cpu().numpy(), F_dev[3], symmetric=True)
+    p_ee = syn.pair_counts(E_dev[1].cpu().numpy(), E_dev[2], symmetric=False)
+    p_ef = e_pack.pair_count(f_pack)
+    N = e_pack.n_groups + 3 * f_pack.n_groups
+    del E_dev, F_dev
+    gp = GP(kernel=RBF_mb(para=[SIGMA, ELL], zeta=ZETA), descriptor=des, noise_e=NOISE_E, noise_f=NOISE_F, log_file=None)
+    gp.train_x = {"energy": e_pack, "force": f_pack}
+    gp.y_train = syn.targets(labelled)
+    out = gp._build_K(grad=True)       # warm-up
+    del out
+    torch.cuda.synchronize()
+    _lib.PROFILE = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    out = gp._build_K(grad=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    del out
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    ms = ev0.elapsed_time(ev1)
+    kff_ms = sum(a.elapsed_time(b) for n, a, b, _ in prof if n == "gprb_kff")
+    peak = np.zeros(1)
+    _lib.call("gprb_fp64_dmma_peak", peak.ctypes.data, gdev.stream())
+    res = {"workload": desc, "N": int(N), "k_build_ms": ms, "gflops": flops_of(p_ff, p_ef, p_ee) / ms * 1e-6,
+           "kff_ms": kff_ms, "kff_frac_of_dmma_peak": 32.0 * D * p_ff / (kff_ms * 1e-3) * 1e-12 / float(peak[0])}
+    # one full GP.fit(opt=True, maxiter) from the default hyper-parameters; a wall budget stops a long optimisation
+    evals, t_start = [], time.perf_counter()
+    orig = gp.log_marginal_likelihood
+
+    class _Budget(Exception):
+        pass
+
+    def counted(params, eval_gradient=False, clone_kernel=False):
+        if evals and time.perf_counter() - t_start > budget_s:
+            raise _Budget()
+        t0 = time.perf_counter()
+        r = orig(params, eval_gradient=eval_gradient, clone_kernel=clone_kernel)
+        torch.cuda.synchronize()
+        evals.append(time.perf_counter() - t0)
+        return r
+
+    gp.log_marginal_likelihood = counted
+    stopped = False
+    with contextlib.redirect_stdout(io.StringIO()):
+        try:
+            gp.fit(opt=True, show=False, maxiter=maxiter)
+        except _Budget:
+            stopped = True
+    torch.cuda.synchronize()
+    res["fit"] = {"call": "GP.fit(opt=True, maxiter=%d)" % maxiter, "wall_s": time.perf_counter() - t_start,
+                  "lml_evaluations": len(evals), "s_per_lml_evaluation": float(np.mean(evals)) if evals else None,
+                  "stopped_by_wall_budget": stopped, "budget_s": budget_s,
+                  "theta": [float(v) for v in gp.kernel.parameters()]}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -189,6 +441,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--predict-structures", type=int, default=10000, help="test structures of the prediction leg")
+    ap.add_argument("--no-small", action="store_true", help="skip the small-N retrain-latency block (BASELINE configs 1-3)")
+    ap.add_argument("--no-s4", action="store_true", help="skip the S4 block (BASELINE config 4) of the 1-GPU run")
+    ap.add_argument("--s4-maxiter", type=int, default=10)
     ap.add_argument("--profile-e2e", default=None, help="write a cProfile listing of one end-to-end step to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -204,7 +460,7 @@ def main():
         if rank != 0:
             return
         n_cpu = args.cpu_structures or 5
-        gf, dt, kind, sample = run_cpu(n_cpu, nrep, seed0, args.steps, max(args.warmup, 0), threads)
+        gf, dt, kind, sample, _ = run_cpu(n_cpu, nrep, seed0, args.steps, max(args.warmup, 0), threads)
         print(json.dumps({"impl": "reference", "metric": "covariance_build_gflops", "value": gf, "unit": "GFLOP/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -374,46 +630,60 @@ def main():
         del gp2
         gdev.clear_cache()
 
-    # ---- predictions per second against the full training set (rank 0's share; replicas scale linearly) ----
+    # ---- predictions per second against the full training set: BASELINE config 5, "predict 10k structures" ----------
+    # 10 000 distinct S5-like test structures (seeds 3000 + k), sharded over the ranks by GP.predict_structures (contiguous
+    # blocks, one all-reduce of the results); wall clock from host Atoms to numpy E / F / sigma on every rank.
     if not args.no_predict:
-        with_io = None
-        predict_parts = {}
         try:
             gp._alpha_dev = None
             K, _, _ = gp._build_K(grad=False)
             K = gp._own(K)
             gp._alpha_dev = gp._factor(K, NOISE_E, NOISE_F)
-            gp._L_dev, gp._Kinv_dev = K, None            # (K is an owned copy, see below)
-            gp.set_K_inv()
-            n_test = 64
-            tests = [a for a, _, _ in syn.structures(n_test, nrep, seed0 + 1000)]
+            gp._L_dev, gp._Kinv_dev = K, None            # (K is an owned copy)
+            gp.fits += 1
+            n_test = args.predict_structures
+            tests = [a for a, _, _ in syn.structures(n_test, nrep, 3000)]
+            # single-structure calls (the reference's route: explicit inverse) on rank-local replicas
             for a in tests[:2]:
                 gp.predict_structure(a, stress=False, return_std=True, f_tol=1e-12)
             barrier()
             t0 = time.perf_counter()
-            for a in tests[:8]:
-                single = gp.predict_structure(a, stress=False, return_std=True, f_tol=1e-12)
+            singles = [gp.predict_structure(a, stress=False, return_std=True, f_tol=1e-12) for a in tests[:8]]
             barrier()
             single_ms = (time.perf_counter() - t0) / 8 * 1e3
-            gp.predict_structures(tests[:32], return_std=True, f_tol=1e-12, batch=32)
+            gp.predict_structures(tests[:64 * world], return_std=True, f_tol=1e-12, batch=32)      # warm-up (and the route probe)
             barrier()
             _lib.PROFILE = []
             t0 = time.perf_counter()
             res = gp.predict_structures(tests, return_std=True, f_tol=1e-12, batch=32)
             barrier()
-            with_io = n_test / (time.perf_counter() - t0)
+            dt_pred = time.perf_counter() - t0
             prof, _lib.PROFILE = _lib.PROFILE, None
+            t = torch.tensor([dt_pred], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_pred = float(t[0])
+            predict_parts = {}
+            n_batches = max(1, -(-(-(-n_test // world)) // 32))       # ceil(ceil(n_test / world) / 32) batches on the busiest rank
             for n, a, b, h in prof:
-                predict_parts[n] = round(predict_parts.get(n, 0.0) + a.elapsed_time(b) / (n_test / 32), 3)
-            assert abs(res[7][0] - single[0]) <= 1e-8 and np.abs(res[7][1] - single[1]).max() <= 1e-8
+                predict_parts[n] = round(predict_parts.get(n, 0.0) + a.elapsed_time(b) / n_batches, 3)
+            dE = max(abs(res[k][0] - singles[k][0]) for k in range(8))
+            dF = max(float(np.abs(res[k][1] - singles[k][1]).max()) for k in range(8))
+            dS = max(max(abs(res[k][3] - singles[k][3]), float(np.abs(res[k][4] - singles[k][4]).max())) for k in range(8))
+            assert len(res) == n_test and dE <= 1e-8 and dF <= 1e-8, (dE, dF)
+            probe = getattr(gp, "_variance_probe", None)
+            result["predict"] = {"value": n_test / dt_pred, "unit": "structures/s", "structures": n_test, "seconds": dt_pred,
+                                 "n_train": N, "atoms": len(tests[0]), "single_call_ms": single_ms,
+                                 "device_ms_per_batch_of_32": predict_parts,
+                                 "batch_vs_single_max_abs": {"E": dE, "F": dF, "sigma": dS},
+                                 "variance_route": None if probe is None else probe[1],
+                                 "variance_probe_sigma_diff": None if probe is None else probe[2],
+                                 "sharding": "structures in contiguous blocks over %d rank(s), results all-reduced" % world,
+                                 "call": "GP.predict_structures(%d Atoms, return_std=True, batch=32): SO3 + K* + mean + std on device, "
+                                         "host Atoms in, numpy E/F/std out on every rank; single_call_ms = one "
+                                         "GP.predict_structure(atoms, stress=False, return_std=True)" % n_test}
         except Exception as exc:      # the prediction leg must not hide the covariance numbers
             result["predict_error"] = repr(exc)
-        if with_io is not None:
-            result["predict"] = {"value": with_io * world, "unit": "structures/s", "n_train": N, "atoms": len(tests[0]),
-                                 "single_call_ms": single_ms, "device_ms_per_batch_of_32": predict_parts,
-                                 "call": "GP.predict_structures(list of Atoms, return_std=True, batch=32): SO3 + K* + mean + std on "
-                                         "device, host Atoms in, numpy E/F/std out; every rank predicts its own share (replicas); "
-                                         "single_call_ms = one GP.predict_structure(atoms, stress=False, return_std=True)"}
 
     # ---- descriptor producer: SO3 of the whole training set on the device (host Atoms in, device x / dxdr / seq out) ----
     atoms_list = [a for a, _, _ in labelled]

@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpr_b200.so")
+# GPRB_LIB: another build of the same library (kernel A/B experiments, tools/build_variant.sh); the default is the in-tree build
+LIB_PATH = os.environ.get("GPRB_LIB") or os.path.join(_HERE, "libgpr_b200.so")
 
 c_int, c_ll, c_dbl, c_vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_void_p
 c_int_p = ctypes.POINTER(ctypes.c_int)

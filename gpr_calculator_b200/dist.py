@@ -144,6 +144,47 @@ def all_reduce_sum(values, device="cpu", group=None):
     return [float(v) for v in t.cpu()]
 
 
+def all_reduce_array(values, device="cpu", group=None):
+    """Element-wise sum of a 1-D float64 numpy array over ranks (sharded prediction: every rank fills its own slots of a
+    zero array, so the sum is an exact gather)."""
+    rank, size = world()
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    if size == 1:
+        return values
+    t = torch.from_numpy(values).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def gather_predictions(mine, n_atoms, first, return_std, device="cpu", group=None):
+    """Combine per-rank prediction results into the full list on every rank.
+
+    mine: this rank's results for the structures [first, first + len(mine)) of a list whose structures have
+    n_atoms[k] atoms: tuples (E, F [n, 3], None) or (E, F, None, E_std, F_std [n, 3]).  Flat layout per structure:
+    E, F (3 n) [, E_std, F_std (3 n)]; every rank fills its own slots of a zero buffer, one all-reduce."""
+    width = 2 if return_std else 1
+    sizes = np.array([(1 + 3 * n) * width for n in n_atoms], dtype=np.int64)
+    offs = np.concatenate(([0], np.cumsum(sizes)))
+    flat = np.zeros(int(offs[-1]))
+    for k, res in enumerate(mine):
+        o, n3 = int(offs[first + k]), 3 * n_atoms[first + k]
+        flat[o] = res[0]
+        flat[o + 1:o + 1 + n3] = np.asarray(res[1]).reshape(-1)
+        if return_std:
+            flat[o + 1 + n3] = res[3]
+            flat[o + 2 + n3:o + 2 + 2 * n3] = np.asarray(res[4]).reshape(-1)
+    flat = all_reduce_array(flat, device=device, group=group)
+    out = []
+    for k, n in enumerate(n_atoms):
+        o, n3 = int(offs[k]), 3 * n
+        F = flat[o + 1:o + 1 + n3].reshape(-1, 3).copy()
+        if return_std:
+            out.append((float(flat[o]), F, None, float(flat[o + 1 + n3]), flat[o + 2 + n3:o + 2 + 2 * n3].reshape(-1, 3).copy()))
+        else:
+            out.append((float(flat[o]), F, None))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # fused gather: K of every rank mapped into every process (CUDA IPC over NVLink peer access)
 # ------------------------------------------------------------------------------------------------

@@ -539,29 +539,53 @@ class GP():
         mean, var = self._mean_var(K_trans, diag)
         return K_trans, mean, var
 
-    # rows of K* from which the variance goes through the Cholesky factor (one trsm, m N^2 flops) instead of
-    # the explicit inverse (gemm, 2 m N^2 flops, gaussianprocess.py:369,905): a triangular solve with few
-    # right-hand sides is latency bound (S5: m = 97: 15 ms vs 8 ms; m = 582: 31 vs 37 ms; m = 3104: 113 vs 190 ms,
-    # tools/predict_routes.py), so single structures keep the reference's route
+    # Variance routes.  The reference multiplies K* with the explicit inverse (gaussianprocess.py:369, 905: "inverse",
+    # gprb_predict: gemm, 2 m N^2 flops); |L^-1 k*|^2 through the Cholesky factor ("chol", gprb_predict_chol: one trsm, m N^2
+    # flops, no N x N inverse) is algebraically the same number.  A triangular solve with few right-hand sides is latency
+    # bound (S5: m = 97: 15 ms vs 8 ms; m = 3104: 113 vs 190 ms, tools/predict_routes.py), so below this many rows of K*
+    # (single structures) the reference's route is always used.  For larger batches the factor route is used only if it
+    # reproduces the reference's route to SIGMA_TOL in the standard deviation on a probe of the first rows after each fit
+    # (both routes lose cond(K) eps in the cancellation diag - k*^T K^-1 k*; when that exceeds 1e-8 the reference's own
+    # arithmetic is the one to follow).  GPRB_VARIANCE_ROUTE = chol | inverse overrides the probe.
     CHOL_VARIANCE_MIN_ROWS = 512
+    SIGMA_TOL = 1e-8
+    PROBE_ROWS = 128
+
+    def _batch_variance_route(self, K_trans, diag):
+        route = os.environ.get("GPRB_VARIANCE_ROUTE", "auto")
+        if route in ("chol", "inverse"):
+            return route
+        probe = getattr(self, "_variance_probe", None)
+        if probe is None or probe[0] != self.fits:
+            m, N = min(K_trans.shape[0], self.PROBE_ROWS), K_trans.shape[1]
+            Kp, dp = K_trans[:m], diag[:m]
+            mean, work = torch.empty(m, dtype=F64, device="cuda"), torch.empty((m, N), dtype=F64, device="cuda")
+            v_c, v_i = torch.empty(m, dtype=F64, device="cuda"), torch.empty(m, dtype=F64, device="cuda")
+            self.set_K_inv()
+            _lib.call("gprb_predict_chol", m, N, ptr(Kp), K_trans.stride(0), ptr(self._alpha_dev), ptr(self._L_dev), N,
+                      ptr(dp), ptr(mean), ptr(v_c), ptr(work), stream())
+            _lib.call("gprb_predict", m, N, ptr(Kp), K_trans.stride(0), ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
+                      ptr(dp), ptr(mean), ptr(v_i), ptr(work), stream())
+            diff = float((torch.sqrt(v_c) - torch.sqrt(v_i)).abs().max())
+            probe = self._variance_probe = (self.fits, "chol" if diff <= self.SIGMA_TOL else "inverse", diff)
+        return probe[1]
 
     def _mean_var(self, K_trans, diag):
         """mean = K* alpha and, when `diag` (the prior variances) is given, var = max(diag - k*^T K^-1 k*, 0)."""
         m, N = K_trans.shape
         mean = torch.empty(m, dtype=F64, device="cuda")
         if diag is None:
-            _lib.call("gprb_predict", m, N, ptr(K_trans), N, ptr(self._alpha_dev), c_vp(0), N, c_vp(0), ptr(mean), c_vp(0),
-                      c_vp(0), stream())
+            _lib.call("gprb_predict", m, N, ptr(K_trans), K_trans.stride(0), ptr(self._alpha_dev), c_vp(0), N, c_vp(0), ptr(mean),
+                      c_vp(0), c_vp(0), stream())
             return mean, None
         var = torch.empty(m, dtype=F64, device="cuda")
         work = torch.empty((m, N), dtype=F64, device="cuda")
-        route = os.environ.get("GPRB_VARIANCE_ROUTE", "auto")          # auto | chol | inverse
-        if self._L_dev is not None and (route == "chol" or (route == "auto" and m >= self.CHOL_VARIANCE_MIN_ROWS)):
-            _lib.call("gprb_predict_chol", m, N, ptr(K_trans), N, ptr(self._alpha_dev), ptr(self._L_dev), N,
+        if self._L_dev is not None and m >= self.CHOL_VARIANCE_MIN_ROWS and self._batch_variance_route(K_trans, diag) == "chol":
+            _lib.call("gprb_predict_chol", m, N, ptr(K_trans), K_trans.stride(0), ptr(self._alpha_dev), ptr(self._L_dev), N,
                       ptr(diag), ptr(mean), ptr(var), ptr(work), stream())
         else:
             self.set_K_inv()
-            _lib.call("gprb_predict", m, N, ptr(K_trans), N, ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
+            _lib.call("gprb_predict", m, N, ptr(K_trans), K_trans.stride(0), ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
                       ptr(diag), ptr(mean), ptr(var), ptr(work), stream())
         return mean, var
 
@@ -942,16 +966,30 @@ class GP():
             return E, F, S, y_std[0], F_std
         return E, F, S
 
-    def predict_structures(self, strucs, return_std=False, f_tol=1e-8, batch=32):
+    def predict_structures(self, strucs, return_std=False, f_tol=1e-8, batch=32, shard=True):
         """Batched predict_structure(stress=False): descriptors, K*, mean and variance of `batch`
         structures per device pass (the "predict 10k structures" path of the benchmark).
+
+        Multi-GPU (torch.distributed initialised, every rank holds the fitted model and calls this with the same
+        list): the structures are sharded over the ranks in contiguous blocks balanced by atom count, every rank
+        predicts its block and the results are combined with one all-reduce of a [sum(1 + 3 n) x (1 or 2)] buffer in
+        which each rank fills only its own slots (replaces the reference's per-structure rank-0 evaluation + bcast,
+        gaussianprocess.py:834-918 under mpi4py).  shard=False: every rank predicts the whole list (replicas).
 
         Returns a list of (E, F, None) or (E, F, None, E_std, F_std) tuples, one per structure, equal to
         what predict_structure returns for each of them."""
         require_cuda()
-        from .batch import rows_from_batch
         if self.base_potential is not None:
             raise NotImplementedError("base potentials are outside the B200 hot path")
+        rank, size = gdist.world()
+        if size == 1 or not shard or len(strucs) == 0:
+            return self._predict_structures_local(strucs, return_std, f_tol, batch)
+        bounds = gdist.split_groups([len(s_) for s_ in strucs], size)
+        mine = self._predict_structures_local(strucs[bounds[rank]:bounds[rank + 1]], return_std, f_tol, batch)
+        return gdist.gather_predictions(mine, [len(s_) for s_ in strucs], bounds[rank], return_std, device="cuda")
+
+    def _predict_structures_local(self, strucs, return_std, f_tol, batch):
+        from .batch import rows_from_batch
         train_x = self.get_train_x()
         out = []
         for s0 in range(0, len(strucs), batch):

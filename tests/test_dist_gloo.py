@@ -38,6 +38,17 @@ def _worker(rank, size, port, q):
     ok = ok and bool(torch.equal(mine, full))
     wu = gd.row_windows([10] * NE, list(range(20, 20 + NF)), size, upper=True)
     ok = ok and wu[0][1][0] == 0 and wu[-1][1][1] == NF and wu[0][1][1] <= windows[0][1][1]   # early rows cost more
+    # sharded prediction: every rank holds the results of its contiguous block of structures
+    n_atoms = [3, 1, 4, 1, 5, 9, 2]
+    truth = [(float(k), np.full((n, 3), k + 0.5), None, 10.0 + k, np.full((n, 3), k + 0.25)) for k, n in enumerate(n_atoms)]
+    b = gd.split_groups(n_atoms, size)
+    for std in (False, True):
+        got_p = gd.gather_predictions([t if std else t[:3] for t in truth[b[rank]:b[rank + 1]]], n_atoms, b[rank], std)
+        for t, g in zip(truth, got_p):
+            ok = ok and g[0] == t[0] and np.array_equal(g[1], t[1]) and g[2] is None and len(g) == (5 if std else 3)
+            if std:
+                ok = ok and g[3] == t[3] and np.array_equal(g[4], t[4])
+    ok = ok and gd.broadcast_floats([float(rank), 7.0], src=0) == [0.0, 7.0]
     s = gd.all_reduce_sum([float(rank + 1), 2.0])
     q.put((rank, ok, s, gd.world()))
     dist.destroy_process_group()
