@@ -445,6 +445,7 @@ def main():
     ap.add_argument("--no-small", action="store_true", help="skip the small-N retrain-latency block (BASELINE configs 1-3)")
     ap.add_argument("--no-s4", action="store_true", help="skip the S4 block (BASELINE config 4) of the 1-GPU run")
     ap.add_argument("--s4-maxiter", type=int, default=10)
+    ap.add_argument("--s4-budget-s", type=float, default=150.0, help="wall budget of the S4 GP.fit (no new LML evaluation after it)")
     ap.add_argument("--profile-e2e", default=None, help="write a cProfile listing of one end-to-end step to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -514,6 +515,22 @@ def main():
     def step():
         return gp._build_K(grad=True)
 
+    # ---- multi-GPU parity, before anything is timed (the driver's GPU test box has one GPU) -----------
+    parity_multi = None
+    if world > 1:
+        pm = sharded_parity(des, nrep, seed0)
+        t = torch.tensor([pm["max_rel_K"], pm["max_rel_dK"], pm["lml_rel"], pm["grad_rel"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pm.update({"max_rel_K": float(t[0]), "max_rel_dK": float(t[1]), "lml_rel": float(t[2]), "grad_rel": float(t[3])})
+        pm["passed"] = bool(pm["max_rel_K"] <= 1e-12 and pm["max_rel_dK"] <= 1e-12 and pm["lml_rel"] <= 1e-10 and pm["grad_rel"] <= 1e-8)
+        pm["what"] = ("row-sharded K / dK/dl (+ LML and gradient) of a %d-row problem against the window-free build on every "
+                      "rank, max over ranks" % pm["N"])
+        parity_multi = pm
+        if not pm["passed"]:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU parity failed", "parity_multi": pm}))
+            raise SystemExit(3)
+
     for _ in range(max(args.warmup, 0)):
         out = step()
         del out
@@ -567,6 +584,10 @@ def main():
               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
               "config": config, "roofline": roofline, "gpu_launches": int(launches), "clocks": clk,
               "k_build_ms": ms_step, "kff_ms_max_over_ranks": kff_ms_max}
+    if parity_multi is not None:
+        result["parity_multi"] = parity_multi
+    if world > 1 and getattr(gp, "_peer", None) is None and gdist.peer_gather_enabled():
+        result["config"]["gather"] = "NCCL all-gather (peer mapping unavailable)"
 
     # ---- end to end: GP.log_marginal_likelihood from pinned host arrays ------------------------------
     if not args.no_e2e:
@@ -702,17 +723,34 @@ def main():
                      "call": "SO3.calculate_batch(64 structures, to_host=False): neighbour search, radial integrals, power spectrum "
                              "and dx/dr on device; bound by FP64 special functions, not HBM"}
 
-    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ------------------------------------
+    # ---- small-N retrain latency (BASELINE configs 1-3) and S4 (config 4): 1-GPU run only ---------------------------
+    if world == 1 and not args.no_small:
+        try:
+            result["small_n"] = small_n_block(des)
+        except Exception as exc:
+            result["small_n_error"] = repr(exc)
+    if world == 1 and not args.no_s4 and args.workload == "s5":
+        try:
+            del gp, e_pack, f_pack, E_dev, F_dev
+            gdev.clear_cache()
+            torch.cuda.empty_cache()
+            result["s4"] = s4_block(des, args.s4_maxiter, args.s4_budget_s)
+        except Exception as exc:
+            result["s4_error"] = repr(exc)
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) + parity of the CUDA path against it -------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = args.cpu_structures or 8
-        gf, dt, kind, sample = run_cpu(n_cpu, nrep, seed0, 1, 0, threads)
+        gf, dt, kind, sample, (e_items, f_items, ref) = run_cpu(n_cpu, nrep, seed0, 1, 0, threads)
         result["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample,
                                   "seconds": dt}
         if SO3_CPU_SECONDS:
             result["so3"]["cpu_port_structures_per_s"] = 1.0 / float(np.mean(SO3_CPU_SECONDS))
             result["so3"]["cpu_port"] = "oracle/so3.py (numpy restatement of SO3.calculate), 1 core, same structures"
-    if world > 1 and getattr(gp, "_peer", None) is None and gdist.peer_gather_enabled():
-        result["config"]["gather"] = "NCCL all-gather (peer mapping unavailable)"
+        result["parity"] = parity_vs_reference(e_items, f_items, ref[0], ref[1], [syn.cu_fcc(nrep, seed0 + k)[0] for k in range(n_cpu)])
+        if not result["parity"]["passed"]:
+            print(json.dumps({"error": "parity against the reference failed", "parity": result["parity"]}))
+            raise SystemExit(4)
     if rank == 0:
         print(json.dumps(result))
     if world > 1:

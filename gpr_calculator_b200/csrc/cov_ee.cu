@@ -5,7 +5,8 @@
 // dot_kernel.py:46), and the numpy K_ee_RBF / K_ee used only by diag()
 // (kernels/base.py:107-130, Dot_mb.py:177-202).
 //
-// 2*d flops per pair: a small fraction of any fit, so this is a plain
+// Scalar kernels: the eps-regularised diagonal, and K_ee for descriptors longer than 32 (the DMMA route of
+// gprb_kee lives in cov_mma.cu).  2*d flops per pair, a plain
 // DFMA kernel: one CTA per (row group I, column-group slice), the rows of I staged in shared
 // memory, one warp per column group J, lanes over the pairs; fixed-order reductions.
 #include "common.cuh"
@@ -149,9 +150,9 @@ int fill(EEParams &P, int kernel, double p0, double p1, double zeta) {
 
 }  // namespace
 
-extern "C" int gprb_kee(int kernel, const gprb_pack *e1, const gprb_pack *e2, double p0, double p1, double zeta,
-                        int grp_begin, int grp_end, double *K, long long ldk, double *dK, long long lddk, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+// scalar K_ee (any descriptor length that fits the staging buffer): the route of gprb_kee (cov_mma.cu) for d > 32
+int gprb_kee_scalar(int kernel, const gprb_pack *e1, const gprb_pack *e2, double p0, double p1, double zeta,
+                    int grp_begin, int grp_end, double *K, long long ldk, double *dK, long long lddk, cudaStream_t st) {
     GPRB_REQUIRE(e1 && e2 && K, "gprb_kee: NULL argument");
     { int rcd = gprb_check_device(e1, "gprb_kee"); if (rcd || (rcd = gprb_check_device(e2, "gprb_kee"))) return rcd; }
     GPRB_REQUIRE(e1->ncols == 0 && e2->ncols == 0, "gprb_kee: both sides must be energy packs");

@@ -54,6 +54,8 @@ struct CovParams {
     int win_r0, win_r1;                                   // row window on side A (flat rows)
     // k1 = sigma^2/(2 l^2), kz = k1*zeta, c = 1/(2 l^2), h0 = 1/l^3 - 2/l ; Dot: c_dot = sigma^2 zeta
     double k1, kz, c, c_il3, h0, zeta, tol, c_dot;
+    double s2, s02;                                          // EE blocks: sigma^2 and (Dot) sigma0^2
+    const int *group_rowsA;                                  // EE blocks: rows per group of side A (1 / (n_I n_J))
     int zi, use_tol, mode, grp_begin;
     double *K; long long ldk; double *dK; long long lddk;     // kff: K / dK/dl ; kfe: Kfe / dKfe
     double *K2; long long ldk2; double *dK2; long long lddk2; // kfe only: Kef / dKef (transposed copies)
@@ -142,11 +144,22 @@ __device__ __forceinline__ double pow_zm2(double s, double zeta, int zi) {
 
 // Per-pair scalar weights.  out = w1*G + w2*p q^T ; grad: dout = u1*G + u2*p q^T
 // (for NB == 1: out_c = w1 * p_c, dout_c = u1 * p_c).  `valid` may be cleared by the pair cut.
-template <int KERNEL, bool GRAD, bool FF, int ZI>
+template <int KERNEL, bool GRAD, bool FF, int ZI, bool EE = false>
 __device__ __forceinline__ void pair_weights(const CovParams &P, const double *tab, double s, bool &valid,
                                              double &w1, double &w2, double &u1, double &u2) {
     const double sm2 = pow_zm2<ZI>(s, P.zeta, P.zi);
     const double sm1 = s * sm2;
+    if (EE) {
+        // energy-energy pair: w1 = k(a, b), u1 = dk/dl = k (1 - D) / l^3   (rbf_kernel.cpp:40-47, 86-94; dot_kernel.cpp:38-44)
+        const double D = s * sm1;
+        if (KERNEL == GPRB_KERNEL_RBF) {
+            w1 = P.s2 * exp_neg(fma(D, P.c, -P.c), tab);
+            if (GRAD) u1 = w1 * fma(-P.c_il3, D, P.c_il3);
+        } else {
+            w1 = P.s2 * (D + P.s02);
+        }
+        return;
+    }
     if (KERNEL == GPRB_KERNEL_RBF) {
         // every weight is E times a factor that does not depend on E: the factors are computed next to the exp
         // chain (instruction-level parallelism), one multiply each once E is known
@@ -215,14 +228,17 @@ _Pragma("unroll") \
                 flush_idx++; \
     } while (0)
 
+// NB = component tiles per column tile: 4 = force columns against force rows (K_ff), 1 = energy columns against force
+// rows (K_fe / K_ef), 0 = energy columns against ENERGY rows (K_ee: one component on both sides, two CTAs per SM)
 template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI, bool TWO>
-__global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) {
-    constexpr bool FF = (NB == 4);
-    constexpr int NOUT = FF ? 9 : 3;
+__global__ void __launch_bounds__(THREADS, NB == 0 ? 2 : 1) cov_mma_kernel(const CovParams P) {
+    constexpr bool FF = (NB == 4), EE = (NB == 0);
+    constexpr int NA = EE ? 1 : 4, NBC = EE ? 1 : NB;        // component tiles of a row tile / of a column tile
+    constexpr int NOUT = FF ? 9 : (EE ? 1 : 3);
     constexpr int NT = GRAD ? 2 * NOUT : NOUT;
     constexpr int N1 = (NT + 1) / 2, N2 = (N1 + 1) / 2;      // values left after each transposing butterfly step
     const int KS = KS_T ? KS_T : P.ks;
-    const int a_tile_d = 4 * KS * 32, b_tile_d = NB * KS * 32;
+    const int a_tile_d = NA * KS * 32, b_tile_d = NBC * KS * 32;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sA = reinterpret_cast<double *>(smem_raw);                  // [WARPS][a_tile_d]
@@ -350,6 +366,20 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                         if (shared) atomicAdd(qt, v); else *qt = v;
                     }
                 }
+            } else if (EE) {
+                // K_ee[I, J] = 1 / (n_I n_J) sum k   (rbf_kernel.py:56-70, dot_kernel.py:46); symmetric mode mirrors
+                const double nn = (double)P.group_rowsA[I] * (double)P.group_rowsB[J];
+                const double val = nn > 0 ? v / nn : 0.0;
+                double *dst = isgrad ? P.dK : P.K;
+                const long long ld = isgrad ? P.lddk : P.ldk;
+                if (!(P.mode == GPRB_FF_SYMMETRIC && J < I)) {
+                    double *qd = dst + (long long)(I - P.grp_begin) * ld + J;
+                    if (shared) atomicAdd(qd, val); else *qd = val;
+                    if (P.mode == GPRB_FF_SYMMETRIC && J > I) {
+                        double *qt = dst + (long long)J * ld + I;
+                        if (shared) atomicAdd(qt, val); else *qt = val;
+                    }
+                }
             } else {
                 // a side = force group I (window), b side = energy group J; K_ef = -(1/n_J) sum
                 const int nJ = P.group_rowsB[J];
@@ -460,48 +490,68 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                 continue;
             }
 
-            double acc[4][NB][2];
+            // species of this thread's two pairs (a = ra, b = 2*q4 + j): read after the DMMAs, except for K_ee
+            bool valid[2];
+            if (EE) {
+                const int2 eb = *reinterpret_cast<const int2 *>(rec + 2 * q4);
+                valid[0] = (ele_a == eb.x) && (ele_a >= 0);
+                valid[1] = (ele_a == eb.y) && (ele_a >= 0);
+                // energy rows of one structure are usually ordered by species (all Mg, all O, ...): a pair of tiles without any
+                // same-species pair contributes nothing (rbf_kernel.cpp:26-37) -- skip its DMMAs and exp; a group that ends in
+                // the tile still has to be flushed
+                if (!__any_sync(0xffffffffu, valid[0] || valid[1])) {
+                    const int nseg0 = rec[8];
+                    for (int sg = 0; sg < nseg0; sg++) {
+                        const int J = rec[10 + 2 * sg], mf = rec[11 + 2 * sg];
+                        if (J < ga || J >= gb || !(mf & 0x100)) continue;
+                        COV_FLUSH_GROUP(J);
+                    }
+                    continue;
+                }
+            }
+            double acc[NA][NBC][2];
 #pragma unroll
-            for (int c = 0; c < 4; c++)
+            for (int c = 0; c < NA; c++)
 #pragma unroll
-                for (int e = 0; e < NB; e++) { acc[c][e][0] = 0.0; acc[c][e][1] = 0.0; }
+                for (int e = 0; e < NBC; e++) { acc[c][e][0] = 0.0; acc[c][e][1] = 0.0; }
             if (KS_T) {
 #pragma unroll
                 for (int k = 0; k < (KS_T ? KS_T : 1); k++) {
-                    double af[4], bf[NB];
+                    double af[NA], bf[NBC];
 #pragma unroll
-                    for (int c = 0; c < 4; c++) af[c] = pa[(c * KS_T + k) * 32];
+                    for (int c = 0; c < NA; c++) af[c] = pa[(c * KS_T + k) * 32];
 #pragma unroll
-                    for (int e = 0; e < NB; e++) bf[e] = pb[(e * KS_T + k) * 32];
+                    for (int e = 0; e < NBC; e++) bf[e] = pb[(e * KS_T + k) * 32];
 #pragma unroll
-                    for (int c = 0; c < 4; c++)
+                    for (int c = 0; c < NA; c++)
 #pragma unroll
-                        for (int e = 0; e < NB; e++) dmma(acc[c][e][0], acc[c][e][1], af[c], bf[e]);
+                        for (int e = 0; e < NBC; e++) dmma(acc[c][e][0], acc[c][e][1], af[c], bf[e]);
                 }
             } else {
                 for (int k = 0; k < KS; k++) {
-                    double af[4], bf[NB];
+                    double af[NA], bf[NBC];
 #pragma unroll
-                    for (int c = 0; c < 4; c++) af[c] = pa[(c * KS + k) * 32];
+                    for (int c = 0; c < NA; c++) af[c] = pa[(c * KS + k) * 32];
 #pragma unroll
-                    for (int e = 0; e < NB; e++) bf[e] = pb[(e * KS + k) * 32];
+                    for (int e = 0; e < NBC; e++) bf[e] = pb[(e * KS + k) * 32];
 #pragma unroll
-                    for (int c = 0; c < 4; c++)
+                    for (int c = 0; c < NA; c++)
 #pragma unroll
-                        for (int e = 0; e < NB; e++) dmma(acc[c][e][0], acc[c][e][1], af[c], bf[e]);
+                        for (int e = 0; e < NBC; e++) dmma(acc[c][e][0], acc[c][e][1], af[c], bf[e]);
                 }
             }
 
-            // weights of this thread's two pairs (a = ra, b = 2*q4 + j), once per tile
-            const int2 eb = *reinterpret_cast<const int2 *>(rec + 2 * q4);
+            // weights of this thread's two pairs, once per tile
+            if (!EE) {
+                const int2 eb = *reinterpret_cast<const int2 *>(rec + 2 * q4);
+                valid[0] = (ele_a == eb.x) && (ele_a >= 0);
+                valid[1] = (ele_a == eb.y) && (ele_a >= 0);
+            }
             double w1[2], w2[2], u1[2], u2[2];
-            bool valid[2];
 #pragma unroll
             for (int j = 0; j < 2; j++) {
-                const int ele_b = j ? eb.y : eb.x;
-                valid[j] = (ele_a == ele_b) && (ele_a >= 0);
                 w2[j] = 0.0; u1[j] = 0.0; u2[j] = 0.0;
-                pair_weights<KERNEL, GRAD, FF, ZI>(P, sTab, acc[0][0][j], valid[j], w1[j], w2[j], u1[j], u2[j]);
+                pair_weights<KERNEL, GRAD, FF, ZI, EE>(P, sTab, acc[0][0][j], valid[j], w1[j], w2[j], u1[j], u2[j]);
             }
 
             const int nseg = rec[8];
@@ -512,16 +562,19 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                 for (int j = 0; j < 2; j++) {
                     const bool on = valid[j] && ((mf >> (2 * q4 + j)) & 1);
                     const double W1 = on ? w1[j] : 0.0;
-                    if (FF) {
+                    if (EE) {
+                        out[0] += W1;
+                        if (GRAD) out[NOUT] += on ? u1[j] : 0.0;
+                    } else if (FF) {
                         const double W2 = on ? w2[j] : 0.0, U1 = on ? u1[j] : 0.0, U2 = on ? u2[j] : 0.0;
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
-                            const double pc = acc[c + 1][0][j];
+                            const double pc = acc[(NA == 4) ? c + 1 : 0][0][j];
                             const double t2 = W2 * pc;
                             const double t3 = GRAD ? U2 * pc : 0.0;
 #pragma unroll
                             for (int e = 0; e < 3; e++) {
-                                const double G = acc[c + 1][(NB == 4) ? e + 1 : 0][j];
+                                const double G = acc[(NA == 4) ? c + 1 : 0][(NB == 4) ? e + 1 : 0][j];
                                 const double qe = acc[0][(NB == 4) ? e + 1 : 0][j];
                                 out[c * 3 + e] = fma(W1, G, fma(t2, qe, out[c * 3 + e]));
                                 if (GRAD) out[NOUT + c * 3 + e] = fma(U1, G, fma(t3, qe, out[NOUT + c * 3 + e]));
@@ -531,7 +584,7 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
                         const double U1 = on ? u1[j] : 0.0;
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
-                            const double pc = acc[c + 1][0][j];
+                            const double pc = acc[(NA == 4) ? c + 1 : 0][0][j];
                             out[c] = fma(W1, pc, out[c]);
                             if (GRAD) out[NOUT + c] = fma(U1, pc, out[NOUT + c]);
                         }
@@ -555,8 +608,9 @@ __global__ void __launch_bounds__(THREADS, 1) cov_mma_kernel(const CovParams P) 
 }
 
 size_t cov_smem_bytes(int nb, int ks, bool grad) {
-    const int nt = (nb == 4 ? 9 : 3) * (grad ? 2 : 1);
-    return (size_t)(WARPS * 4 * ks * 32 + STAGES * CH * nb * ks * 32 + NFB * MAXROWS * nt + 32) * 8 +
+    const int nt = (nb == 4 ? 9 : (nb == 0 ? 1 : 3)) * (grad ? 2 : 1);
+    const int na = nb == 0 ? 1 : 4, nbc = nb == 0 ? 1 : nb;
+    return (size_t)(WARPS * na * ks * 32 + STAGES * CH * nbc * ks * 32 + NFB * MAXROWS * nt + 32) * 8 +
            (size_t)MAXROWS * 16 + (size_t)STAGES * CH * REC * 4 + (STAGES + 1 + NFB) * 8 + STAGES * 4 + 128;
 }
 
@@ -683,6 +737,8 @@ int fill_kernel_params(CovParams &P, int kernel, double p0, double p1, double ze
         P.c = P.k1 = P.kz = P.c_il3 = P.h0 = 0.0;
     }
     P.c_dot = p0 * p0 * zeta;
+    P.s2 = p0 * p0;
+    P.s02 = kernel == GPRB_KERNEL_DOT ? p1 * p1 : 0.0;
     return upload_tables();
 }
 
@@ -837,4 +893,47 @@ extern "C" int gprb_kfe_multi(int kernel, const gprb_pack *e, const gprb_pack *f
     GPRB_REQUIRE(Kfe_dst_host && n_dst >= 1 && Kfe_dst_host[0], "gprb_kfe_multi: NULL destination");
     return kef_impl(kernel, e, f, p0, p1, zeta, grp_begin, grp_end, nullptr, 0, n_dst, Kfe_dst_host, ld_fe, nullptr, 0, dKfe, ld_dfe,
                     (cudaStream_t)stream);
+}
+
+// K_ee on the same tile machinery (NB = 0: one component per side, 8 DMMAs per 8 x 8 pairs, table exp, tiles without a
+// same-species pair skipped).  Replaces rbf_kee_many / rbf_kee_many_with_grad (rbf_kernel.cpp:5-98) and dot_kee_many
+// (dot_kernel.cpp:5-56) with the wrappers' 1 / (n_I n_J) (rbf_kernel.py:56-70, dot_kernel.py:46).  Descriptors longer than
+// 32 take the scalar kernel of cov_ee.cu.
+int gprb_kee_scalar(int kernel, const gprb_pack *e1, const gprb_pack *e2, double p0, double p1, double zeta,
+                    int grp_begin, int grp_end, double *K, long long ldk, double *dK, long long lddk, cudaStream_t st);
+
+extern "C" int gprb_kee(int kernel, const gprb_pack *e1_, const gprb_pack *e2, double p0, double p1, double zeta,
+                        int grp_begin, int grp_end, double *K, long long ldk, double *dK, long long lddk, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    gprb_pack *e1 = const_cast<gprb_pack *>(e1_);
+    GPRB_REQUIRE(e1 && e2 && K, "gprb_kee: NULL argument");
+    { int rcd = gprb_check_device(e1, "gprb_kee"); if (rcd || (rcd = gprb_check_device(e2, "gprb_kee"))) return rcd; }
+    GPRB_REQUIRE(e1->ncols == 0 && e2->ncols == 0, "gprb_kee: both sides must be energy packs");
+    GPRB_REQUIRE(e1->d == e2->d, "gprb_kee: descriptor length mismatch %d vs %d", e1->d, e2->d);
+    GPRB_REQUIRE(kernel == GPRB_KERNEL_RBF || kernel == GPRB_KERNEL_DOT, "gprb_kee: unknown kernel %d", kernel);
+    GPRB_REQUIRE(0 <= grp_begin && grp_begin <= grp_end && grp_end <= e1->n_groups, "gprb_kee: bad window [%d,%d)", grp_begin, grp_end);
+    GPRB_REQUIRE(!(dK && kernel == GPRB_KERNEL_DOT), "gprb_kee: Dot has no dK output (closed form, see header)");
+    if (grp_begin == grp_end || e2->n_groups == 0) return GPRB_OK;
+    if (e1->ks > GPRB_MAX_KS || getenv("GPRB_KEE_SCALAR") != nullptr)      // env: A/B switch of the parity tests
+        return gprb_kee_scalar(kernel, e1, e2, p0, p1, zeta, grp_begin, grp_end, K, ldk, dK, lddk, st);
+    int rc = build_sched(e1, grp_begin, grp_end, st);
+    if (rc) return rc;
+    const int rows = grp_end - grp_begin;
+    GPRB_CUDA(cudaMemset2DAsync(K, ldk * sizeof(double), 0, (size_t)e2->n_groups * sizeof(double), rows, st));
+    if (dK) GPRB_CUDA(cudaMemset2DAsync(dK, lddk * sizeof(double), 0, (size_t)e2->n_groups * sizeof(double), rows, st));
+    if (e1->sched_n == 0 || e2->n_rows == 0) return GPRB_OK;
+    CovParams P = {};
+    rc = fill_kernel_params(P, kernel, p0, p1, zeta);
+    if (rc) return rc;
+    P.PA = e1->P; P.eleA = e1->elep; P.row_groupA = e1->row_group; P.sched = e1->sched; P.sched_ent = e1->sched_ent;
+    P.PB = e2->P; P.recB = e2->tile_rec; P.row_ptrB = e2->d_row_ptr; P.group_rowsB = e2->d_group_rows;
+    P.group_rowsA = e1->d_group_rows;
+    P.n_groupsB = e2->n_groups; P.ks = e1->ks;
+    P.win_r0 = e1->row_ptr[grp_begin]; P.win_r1 = e1->row_ptr[grp_end];
+    // the training block is symmetric: evaluate the J >= I group pairs once and write both entries
+    P.mode = (e1 == e2 && grp_begin == 0 && grp_end == e1->n_groups) ? GPRB_FF_SYMMETRIC : GPRB_FF_FULL;
+    P.grp_begin = grp_begin;
+    P.K = K; P.ldk = ldk; P.dK = dK; P.lddk = lddk;
+    P.n_splits = choose_splits(e1->sched_n, e2->n_groups);
+    return dispatch_cov<0>(kernel, dK != nullptr, P, e1->sched_n, st);
 }

@@ -318,3 +318,86 @@ def test_sparsify_removes_duplicated_points(g):
     n_f2 = len(gp.train_x["force"][-1])
     assert len(gp.train_x["energy"][-1]) == n_e - 1 and n_f - 13 <= n_f2 < n_f
     assert len(gp.y_train) == (n_e - 1) + 3 * n_f2 and gp.alpha_ is not None
+
+
+def _sigma_reference_formula(Kn, Ks, prior):
+    """The reference's arithmetic for the predictive standard deviation on a given noisy training matrix
+    (gaussianprocess.py:128-131 set_K_inv, 904-908): L = cholesky, L_inv = solve_triangular(L.T, I),
+    K_inv = L_inv L_inv^T, var = diag - einsum(K* K_inv, K*), negatives clipped."""
+    from scipy.linalg import cholesky, solve_triangular
+    L = cholesky(Kn, lower=True)
+    L_inv = solve_triangular(L.T, np.eye(len(L)))
+    K_inv = L_inv.dot(L_inv.T)
+    var = prior - np.einsum("ij,ij->i", np.dot(Ks, K_inv), Ks)
+    return np.sqrt(np.maximum(var, 0.0)), L
+
+
+def _sigma_refined(L, Kn, Ks, prior, sweeps=3):
+    """A near-exact value of the same quantity: K z = k* by the Cholesky factor with iterative refinement whose residuals are
+    accumulated in extended precision; var = diag - k* . z."""
+    from scipy.linalg import cho_solve
+    Kl, Kt = Kn.astype(np.longdouble), Ks.T.astype(np.longdouble)
+    Z = cho_solve((L, True), Ks.T).astype(np.longdouble)
+    for _ in range(sweeps):
+        R = Kt - Kl @ Z
+        Z = Z + cho_solve((L, True), R.astype(np.float64)).astype(np.longdouble)
+    var = prior.astype(np.longdouble) - np.einsum("ji,ji->i", Kt, Z)
+    return np.sqrt(np.maximum(var, 0.0)).astype(np.float64)
+
+
+@pytest.mark.timeout(900)
+def test_sigma_routes_against_reference_formula(monkeypatch, capsys):
+    """Pins sigma of both device variance routes in the benchmark's regime (real Cu32 rows, l = 0.1, noise 0.002 / 0.1,
+    N = 24 + 2 304 = 2 328): against the reference's own formula evaluated in numpy / LAPACK on the same K, and against an
+    iteratively refined value.  Tolerances are what each route meets here (printed; recorded in
+    profiles/r02_sigma_routes.txt); the batch route is chosen by GP._batch_variance_route from a probe of exactly this
+    difference, with the reference's route as the fall-back when 1e-8 is not met."""
+    import torch
+    from gpr_calculator_b200 import synthetic as syn, device as gdev
+    from gpr_calculator_b200.gaussianprocess import GP
+    from gpr_calculator_b200.kernels import RBF_mb
+    from gpr_calculator_b200.SO3 import SO3
+    from gpr_calculator_b200.batch import rows_from_batch
+    des = SO3(nmax=3, lmax=4, rcut=5.0)
+    labelled = syn.structures(24, 2, 2000)
+    E_dev, F_dev = syn.packed_from_batch(des, [a for a, _, _ in labelled])
+    gp = GP(kernel=RBF_mb(para=[1.0, 0.1], zeta=2.0), descriptor=des, noise_e=0.002, noise_f=0.1, log_file=None)
+    gp.train_x = {"energy": gdev.Pack(E_dev[0], E_dev[1], E_dev[2]), "force": gdev.Pack(F_dev[0], F_dev[2], F_dev[3], dxdr=F_dev[1])}
+    gp.y_train = syn.targets(labelled)
+    gp.N_energy, gp.N_forces = 24, 24 * 32
+    gp.fit(opt=False, show=False)
+    tests_ = [a for a, _, _ in syn.structures(20, 2, 3000)]          # 20 x 97 = 1 940 rows of K*: the batch routes apply
+    E_t, F_t = rows_from_batch(des.calculate_batch(tests_, to_host=False), None)
+    X = {"energy": gdev.energy_pack(E_t), "force": gdev.force_pack(F_t)}
+    Ks, _ = gp.kernel.k_total_device(X, gp.train_x, f_tol=1e-12, grad=False)
+    prior = gp.kernel.diag_device(X)
+    Kn, _ = gp.kernel.k_total_device(gp.train_x, None, f_tol=1e-10, grad=False)
+    Kn = Kn.cpu().numpy()
+    idx = np.arange(len(Kn))
+    Kn[idx, idx] += np.where(idx < 24, 0.002 ** 2, 0.1 ** 2)
+    Ks_h, prior_h = Ks.cpu().numpy(), prior.cpu().numpy()
+    sig_ref, L = _sigma_reference_formula(Kn, Ks_h, prior_h)
+    sig_true = _sigma_refined(L, Kn, Ks_h, prior_h)
+    got = {}
+    for route in ("inverse", "chol"):
+        monkeypatch.setenv("GPRB_VARIANCE_ROUTE", route)
+        _, var = gp._mean_var(Ks, prior)
+        got[route] = np.sqrt(var.cpu().numpy())
+    monkeypatch.delenv("GPRB_VARIANCE_ROUTE")
+    chosen = gp._batch_variance_route(Ks, prior)
+    d = {"reference formula vs refined": np.abs(sig_ref - sig_true).max(),
+         "device inverse route vs reference formula": np.abs(got["inverse"] - sig_ref).max(),
+         "device chol route vs reference formula": np.abs(got["chol"] - sig_ref).max(),
+         "device inverse route vs refined": np.abs(got["inverse"] - sig_true).max(),
+         "device chol route vs refined": np.abs(got["chol"] - sig_true).max(),
+         "device chol vs device inverse": np.abs(got["chol"] - got["inverse"]).max()}
+    with capsys.disabled():
+        print("\n[sigma routes] N = %d, m = %d, cond(K) = %.3g, sigma range %.3g .. %.3g, probe picks '%s' (diff %.3g)"
+              % (len(Kn), len(sig_ref), np.linalg.cond(Kn), sig_true.min(), sig_true.max(), chosen, gp._variance_probe[2]))
+        for k, v in d.items():
+            print("[sigma routes]   max |d sigma|  %-44s %.3e" % (k, v))
+    # the reference's own formula is only this close to the refined value: no route can be asked for more
+    floor = max(1e-8, 4.0 * d["reference formula vs refined"])
+    assert d["device inverse route vs reference formula"] <= floor
+    assert d["device chol route vs refined"] <= floor
+    assert chosen in ("chol", "inverse") and (chosen == "chol") == (gp._variance_probe[2] <= 1e-8)

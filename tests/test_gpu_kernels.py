@@ -389,3 +389,36 @@ def test_two_stage_path_matches_block_path(monkeypatch):
                 out[two], _ = k_total_device(kern, 1.3, p1, zeta, (None, f), side2, use_tol=True, tol=tol, grad=False, symmetric=sym)
             scale = out[""].abs().max().item()
             assert (out["1"] - out[""]).abs().max().item() <= 1e-12 * scale
+
+
+def test_kee_tensor_path_species_blocks(oracle_libs, monkeypatch):
+    """K_ee on the DMMA tile path in the shape of the Pd4/MgO training set: large energy groups whose rows are ordered by
+    species (tiles without a same-species pair are skipped, also when a group ends inside a skipped tile), ragged group
+    sizes, the symmetric training block and a rectangular window; against the C oracle and against the scalar kernel."""
+    from gpr_calculator_b200.kernels import rbf_kernel as rk, dot_kernel as dk
+    rng = np.random.default_rng(77)
+    base = np.abs(rng.normal(size=30)) + 0.5
+
+    def side(sizes):
+        X, ELE = [], []
+        for n_mg, n_o, n_pd in sizes:
+            n = n_mg + n_o + n_pd
+            X.append(base[None, :] + 0.3 * rng.normal(size=(n, 30)))
+            ELE.append(np.array([12] * n_mg + [8] * n_o + [46] * n_pd))
+        return np.concatenate(X), np.concatenate(ELE), [sum(t) for t in sizes]
+    E1 = side([(108, 108, 4), (108, 108, 4), (50, 61, 1), (3, 0, 9), (0, 17, 0), (108, 108, 4)])
+    E2 = side([(20, 30, 4), (108, 108, 4), (1, 1, 1)])
+    O, OD = oracle_libs.RBFOracle("port"), oracle_libs.DotOracle("port")
+    for a, b in ((E1, E1), (E1, E2), (E2, E1)):
+        for zeta in (2.0, 3.0):
+            ref = O.kee_C(a, b, 1.4, 0.35, zeta, grad=True)
+            monkeypatch.delenv("GPRB_KEE_SCALAR", raising=False)
+            got = rk.kee_C(a, b, 1.4, 0.35, zeta, grad=True)
+            monkeypatch.setenv("GPRB_KEE_SCALAR", "1")
+            old = rk.kee_C(a, b, 1.4, 0.35, zeta, grad=True)
+            monkeypatch.delenv("GPRB_KEE_SCALAR", raising=False)
+            for x, y, z in zip(got, ref, old):
+                assert x.shape == y.shape and rel_err(x, y) <= TOL and rel_err(x, z) <= TOL, zeta
+            assert rel_err(dk.kee_C(a, b, 2.0, 1.5, zeta), OD.kee_C(a, b, 2.0, 1.5, zeta)) <= TOL
+    K = rk.kee_C(E1, E1, 1.4, 0.35, 2.0)
+    assert np.array_equal(K, K.T)
