@@ -323,7 +323,9 @@ def small_n_block(des):
         F_h, _k2 = syn.to_host(F_dev)
         gp = GP(kernel=RBF_mb(para=[SIGMA, ELL], zeta=ZETA), descriptor=des, noise_e=NOISE_E, noise_f=NOISE_F, log_file=None)
         gp.train_x = {"energy": E_h, "force": F_h}
-        gp.y_train = syn.targets(labelled, centres_per_structure=centres)
+        y = syn.targets(labelled, centres_per_structure=centres)
+        gp.train_y = {"energy": list(y[:n_s, 0]), "force": y[n_s:, 0].reshape(-1, 3)}
+        gp.update_y_train()
         gp.N_energy, gp.N_forces = n_s, n_s * centres
         measure(gp, np.array([SIGMA, ELL]), syn.cu_fcc(2, 5000)[0], tag,
                 "%d Cu32 structures: %d E + %d F centres" % (n_s, n_s, n_s * centres))
@@ -380,7 +382,10 @@ def s4_block(des, maxiter, budget_s):
     del E_dev, F_dev
     gp = GP(kernel=RBF_mb(para=[SIGMA, ELL], zeta=ZETA), descriptor=des, noise_e=NOISE_E, noise_f=NOISE_F, log_file=None)
     gp.train_x = {"energy": e_pack, "force": f_pack}
-    gp.y_train = syn.targets(labelled)
+    y = syn.targets(labelled)
+    gp.train_y = {"energy": list(y[:n_struct, 0]), "force": y[n_struct:, 0].reshape(-1, 3)}
+    gp.update_y_train()
+    gp.N_energy, gp.N_forces = e_pack.n_groups, f_pack.n_groups
     out = gp._build_K(grad=True)       # warm-up
     del out
     torch.cuda.synchronize()
@@ -445,7 +450,7 @@ def main():
     ap.add_argument("--no-small", action="store_true", help="skip the small-N retrain-latency block (BASELINE configs 1-3)")
     ap.add_argument("--no-s4", action="store_true", help="skip the S4 block (BASELINE config 4) of the 1-GPU run")
     ap.add_argument("--s4-maxiter", type=int, default=10)
-    ap.add_argument("--s4-budget-s", type=float, default=150.0, help="wall budget of the S4 GP.fit (no new LML evaluation after it)")
+    ap.add_argument("--s4-budget-s", type=float, default=400.0, help="wall budget of the S4 GP.fit (no new LML evaluation after it)")
     ap.add_argument("--profile-e2e", default=None, help="write a cProfile listing of one end-to-end step to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -469,6 +474,13 @@ def main():
                           "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample},
                           "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
+
+    t_bench0 = time.time()
+    block_s = {}
+
+    def mark(name, _last=[time.time()]):
+        block_s[name] = round(time.time() - _last[0], 2)
+        _last[0] = time.time()
 
     import torch
     import torch.distributed as dist
@@ -515,6 +527,7 @@ def main():
     def step():
         return gp._build_K(grad=True)
 
+    mark("setup_descriptors_packs")
     # ---- multi-GPU parity, before anything is timed (the driver's GPU test box has one GPU) -----------
     parity_multi = None
     if world > 1:
@@ -531,6 +544,7 @@ def main():
                 print(json.dumps({"error": "multi-GPU parity failed", "parity_multi": pm}))
             raise SystemExit(3)
 
+    mark("parity_multi")
     for _ in range(max(args.warmup, 0)):
         out = step()
         del out
@@ -589,6 +603,7 @@ def main():
     if world > 1 and getattr(gp, "_peer", None) is None and gdist.peer_gather_enabled():
         result["config"]["gather"] = "NCCL all-gather (peer mapping unavailable)"
 
+    mark("k_build")
     # ---- end to end: GP.log_marginal_likelihood from pinned host arrays ------------------------------
     if not args.no_e2e:
         E_host, keep1 = syn.to_host(E_dev, pin=True)
@@ -651,6 +666,7 @@ def main():
         del gp2
         gdev.clear_cache()
 
+    mark("e2e")
     # ---- predictions per second against the full training set: BASELINE config 5, "predict 10k structures" ----------
     # 10 000 distinct S5-like test structures (seeds 3000 + k), sharded over the ranks by GP.predict_structures (contiguous
     # blocks, one all-reduce of the results); wall clock from host Atoms to numpy E / F / sigma on every rank.
@@ -706,6 +722,7 @@ def main():
         except Exception as exc:      # the prediction leg must not hide the covariance numbers
             result["predict_error"] = repr(exc)
 
+    mark("predict")
     # ---- descriptor producer: SO3 of the whole training set on the device (host Atoms in, device x / dxdr / seq out) ----
     atoms_list = [a for a, _, _ in labelled]
     des.calculate_batch(atoms_list[:64], to_host=False)
@@ -723,12 +740,14 @@ def main():
                      "call": "SO3.calculate_batch(64 structures, to_host=False): neighbour search, radial integrals, power spectrum "
                              "and dx/dr on device; bound by FP64 special functions, not HBM"}
 
+    mark("so3")
     # ---- small-N retrain latency (BASELINE configs 1-3) and S4 (config 4): 1-GPU run only ---------------------------
     if world == 1 and not args.no_small:
         try:
             result["small_n"] = small_n_block(des)
         except Exception as exc:
             result["small_n_error"] = repr(exc)
+    mark("small_n")
     if world == 1 and not args.no_s4 and args.workload == "s5":
         try:
             del gp, e_pack, f_pack, E_dev, F_dev
@@ -738,6 +757,7 @@ def main():
         except Exception as exc:
             result["s4_error"] = repr(exc)
 
+    mark("s4")
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) + parity of the CUDA path against it -------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu = args.cpu_structures or 8
@@ -751,6 +771,8 @@ def main():
         if not result["parity"]["passed"]:
             print(json.dumps({"error": "parity against the reference failed", "parity": result["parity"]}))
             raise SystemExit(4)
+    mark("cpu_baseline_parity")
+    result["bench_seconds"] = dict(block_s, total=round(time.time() - t_bench0, 2))
     if rank == 0:
         print(json.dumps(result))
     if world > 1:

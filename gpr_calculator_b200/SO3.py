@@ -119,8 +119,8 @@ class SO3:
         if isinstance(lmax, int):
             if lmax < 0:
                 raise ValueError('lmax must be greater than or equal to zero')
-            elif lmax > 32:
-                raise NotImplementedError('lmax > 32 is not supported')
+            elif lmax > 15:       # the reference stops at 32 (SO3.py:127); the device kernels hold Y_lm tables up to l = 16
+                raise NotImplementedError('lmax > 15 is not supported by the device kernels')
             self._lmax = lmax
             self._tables = None
         else:

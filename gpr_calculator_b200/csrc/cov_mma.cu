@@ -44,6 +44,7 @@ constexpr int STAGES = 2;
 constexpr int CH = GPRB_CHUNK_TILES;
 constexpr int REC = GPRB_REC_INTS;
 constexpr int MAXROWS = WARPS * 8;
+constexpr int BIG_WARPS = 6, BIG_CH = 2;   // CTA shape of the 9..16 k-step kernels (d = 33..64)
 constexpr int NFB = 4;                 // flush buffers: partials of flush k are summed two flushes later
 
 struct CovParams {
@@ -215,7 +216,7 @@ _Pragma("unroll") \
                     zv[i] += p4 ? tv : 0.0; \
                 } \
                 if (is_head) { \
-                    double *dst = sRow + (size_t)(fb * MAXROWS + arow_local) * NT + q4; \
+                    double *dst = sRow + (size_t)(fb * MAXROWS_K + arow_local) * NT + q4; \
 _Pragma("unroll") \
                     for (int i = 0; i < N2; i++) \
                         if (4 * i + q4 < NT) dst[4 * i] = zv[i]; \
@@ -230,8 +231,11 @@ _Pragma("unroll") \
 
 // NB = component tiles per column tile: 4 = force columns against force rows (K_ff), 1 = energy columns against force
 // rows (K_fe / K_ef), 0 = energy columns against ENERGY rows (K_ee: one component on both sides, two CTAs per SM)
-template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI, bool TWO>
-__global__ void __launch_bounds__(THREADS, NB == 0 ? 2 : 1) cov_mma_kernel(const CovParams P) {
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI, bool TWO, bool BIG>
+__global__ void __launch_bounds__(BIG ? BIG_WARPS * 32 : THREADS, NB == 0 ? 2 : 1) cov_mma_kernel(const CovParams P) {
+    // BIG: descriptors of 33..64 entries (9..16 k-steps): the row tiles of 12 warps no longer fit the shared memory, so 6 warps per CTA and
+    // 2-tile column chunks (functional path for e.g. SO3(nmax=4, lmax=4), d = 50; the benchmarked descriptor has d = 30)
+    constexpr int WARPS_K = BIG ? BIG_WARPS : WARPS, CH_K = BIG ? BIG_CH : CH, MAXROWS_K = WARPS_K * 8;
     constexpr bool FF = (NB == 4), EE = (NB == 0);
     constexpr int NA = EE ? 1 : 4, NBC = EE ? 1 : NB;        // component tiles of a row tile / of a column tile
     constexpr int NOUT = FF ? 9 : (EE ? 1 : 3);
@@ -241,13 +245,13 @@ __global__ void __launch_bounds__(THREADS, NB == 0 ? 2 : 1) cov_mma_kernel(const
     const int a_tile_d = NA * KS * 32, b_tile_d = NBC * KS * 32;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sA = reinterpret_cast<double *>(smem_raw);                  // [WARPS][a_tile_d]
-    double *sB = sA + WARPS * a_tile_d;                                  // [STAGES][CH][b_tile_d]
-    double *sRow = sB + STAGES * CH * b_tile_d;                          // [NFB][MAXROWS][NT] flush partials
-    double *sTab = sRow + NFB * MAXROWS * NT;                            // [32]
-    int4 *sEnt = reinterpret_cast<int4 *>(sTab + 32);                    // [MAXROWS]
-    int *sRec = reinterpret_cast<int *>(sEnt + MAXROWS);                 // [STAGES][CH][REC]
-    uint64_t *sBar = reinterpret_cast<uint64_t *>(sRec + STAGES * CH * REC);   // full[STAGES], A, flush[NFB]
+    double *sA = reinterpret_cast<double *>(smem_raw);                  // [WARPS_K][a_tile_d]
+    double *sB = sA + WARPS_K * a_tile_d;                                  // [STAGES][CH_K][b_tile_d]
+    double *sRow = sB + STAGES * CH_K * b_tile_d;                          // [NFB][MAXROWS_K][NT] flush partials
+    double *sTab = sRow + NFB * MAXROWS_K * NT;                            // [32]
+    int4 *sEnt = reinterpret_cast<int4 *>(sTab + 32);                    // [MAXROWS_K]
+    int *sRec = reinterpret_cast<int *>(sEnt + MAXROWS_K);                 // [STAGES][CH_K][REC]
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(sRec + STAGES * CH_K * REC);   // full[STAGES], A, flush[NFB]
     uint64_t *barFlush = sBar + STAGES + 1;
     int *sCnt = reinterpret_cast<int *>(barFlush + NFB);                 // consumed[STAGES]
 
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, NB == 0 ? 2 : 1) cov_mma_kernel(const
     const int cr0 = P.row_ptrB[ga], cr1 = P.row_ptrB[gb];
     if (cr1 <= cr0) return;
     const int tb0 = cr0 >> 3, tb1 = (cr1 + 7) >> 3;
-    const int c_begin = tb0 / CH, c_end = (tb1 + CH - 1) / CH;
+    const int c_begin = tb0 / CH_K, c_end = (tb1 + CH_K - 1) / CH_K;
 
     if (tid < nent) sEnt[tid] = P.sched_ent[ent0 + tid];
     if (tid < 32) sTab[tid] = c_exp2_tab[tid];
@@ -283,11 +287,11 @@ __global__ void __launch_bounds__(THREADS, NB == 0 ? 2 : 1) cov_mma_kernel(const
     }
     __syncthreads();
 
-    const uint32_t b_chunk_bytes = (uint32_t)(CH * b_tile_d * 8), rec_chunk_bytes = (uint32_t)(CH * REC * 4);
+    const uint32_t b_chunk_bytes = (uint32_t)(CH_K * b_tile_d * 8), rec_chunk_bytes = (uint32_t)(CH_K * REC * 4);
     auto issue = [&](int ci, int buf) {
         mbar_expect_tx(&sBar[buf], b_chunk_bytes + rec_chunk_bytes);
-        bulk_g2s(sB + (size_t)buf * CH * b_tile_d, P.PB + (size_t)ci * CH * b_tile_d, b_chunk_bytes, &sBar[buf]);
-        bulk_g2s(sRec + buf * CH * REC, P.recB + (size_t)ci * CH * REC, rec_chunk_bytes, &sBar[buf]);
+        bulk_g2s(sB + (size_t)buf * CH_K * b_tile_d, P.PB + (size_t)ci * CH_K * b_tile_d, b_chunk_bytes, &sBar[buf]);
+        bulk_g2s(sRec + buf * CH_K * REC, P.recB + (size_t)ci * CH_K * REC, rec_chunk_bytes, &sBar[buf]);
     };
     if (tid == 0) {
         const uint32_t a_bytes = (uint32_t)(ntiles * a_tile_d * 8);
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(THREADS, NB == 0 ? 2 : 1) cov_mma_kernel(const
             const int en = idx / NT, o = idx - en * NT;
             const int4 E4 = sEnt[en];
             const int I = E4.x;
-            const double *src = sRow + (size_t)fb * MAXROWS * NT + o;
+            const double *src = sRow + (size_t)fb * MAXROWS_K * NT + o;
             double v = src[E4.y * NT];
             for (int r = (E4.y & ~7) + 8; r < E4.z; r += 8) v += src[r * NT];
             const bool shared = E4.w != 0;
@@ -410,11 +414,11 @@ __global__ void __launch_bounds__(THREADS, NB == 0 ? 2 : 1) cov_mma_kernel(const
     for (int ci = c_begin; ci < c_end; ci++) {
         const int it = ci - c_begin, buf = it % STAGES;
         mbar_wait(&sBar[buf], (it / STAGES) & 1);
-        for (int tt = 0; tt < CH; tt++) {
-            const int t = ci * CH + tt;
+        for (int tt = 0; tt < CH_K; tt++) {
+            const int t = ci * CH_K + tt;
             if (t < tb0 || t >= tb1) continue;
-            const int *rec = sRec + (buf * CH + tt) * REC;
-            const double *pb = sB + (size_t)(buf * CH + tt) * b_tile_d + lane;
+            const int *rec = sRec + (buf * CH_K + tt) * REC;
+            const double *pb = sB + (size_t)(buf * CH_K + tt) * b_tile_d + lane;
 
             if constexpr (TWO) {
                 // Two-stage contraction (no gradient, d in 29..32; design: profiles/experiments/README.md and
@@ -607,24 +611,26 @@ __global__ void __launch_bounds__(THREADS, NB == 0 ? 2 : 1) cov_mma_kernel(const
     if (flush_idx >= 1) finish(flush_idx - 1, J1);
 }
 
-size_t cov_smem_bytes(int nb, int ks, bool grad) {
+size_t cov_smem_bytes(int nb, int ks, bool grad, bool big) {
     const int nt = (nb == 4 ? 9 : (nb == 0 ? 1 : 3)) * (grad ? 2 : 1);
     const int na = nb == 0 ? 1 : 4, nbc = nb == 0 ? 1 : nb;
-    return (size_t)(WARPS * na * ks * 32 + STAGES * CH * nbc * ks * 32 + NFB * MAXROWS * nt + 32) * 8 +
-           (size_t)MAXROWS * 16 + (size_t)STAGES * CH * REC * 4 + (STAGES + 1 + NFB) * 8 + STAGES * 4 + 128;
+    const int warps = big ? BIG_WARPS : WARPS, ch = big ? BIG_CH : CH, maxrows = warps * 8;
+    return (size_t)(warps * na * ks * 32 + STAGES * ch * nbc * ks * 32 + NFB * maxrows * nt + 32) * 8 +
+           (size_t)maxrows * 16 + (size_t)STAGES * ch * REC * 4 + (STAGES + 1 + NFB) * 8 + STAGES * 4 + 128;
 }
 
 // Row-side schedule for the window [g0, g1): blocks of <= WARPS consecutive flat tiles and, per block, the
 // groups it holds {group, first row, one past last row (block-local), continues in a neighbouring block}.
 int build_sched(gprb_pack *a, int g0, int g1, cudaStream_t st) {
+    const int wpc = a->ks > GPRB_MAX_KS ? BIG_WARPS : WARPS;       // row tiles per CTA of the kernels this pack runs (fixed by its ks)
     if (a->sched_g0 == g0 && a->sched_g1 == g1 && a->sched) return GPRB_OK;
     std::vector<int4> blocks, ents;
     const int r0 = a->row_ptr[g0], r1 = a->row_ptr[g1];
     if (r1 > r0) {
         const int t0 = r0 / 8, t1 = (r1 + 7) / 8;
         int g = g0;
-        for (int tb = t0; tb < t1; tb += WARPS) {
-            const int nt = t1 - tb < WARPS ? t1 - tb : WARPS;
+        for (int tb = t0; tb < t1; tb += wpc) {
+            const int nt = t1 - tb < wpc ? t1 - tb : wpc;
             const int lo = tb * 8 > r0 ? tb * 8 : r0, hi = (tb + nt) * 8 < r1 ? (tb + nt) * 8 : r1;
             const int e0 = (int)ents.size();
             while (g < g1 && a->row_ptr[g + 1] <= lo) g++;      // groups that ended before this block (or empty)
@@ -680,26 +686,30 @@ int upload_tables() {
     return GPRB_OK;
 }
 
-template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI, bool TWO = false>
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool MULTI, bool TWO = false, bool BIG = false>
 int launch_cov_m(const CovParams &P, int n_blocks, cudaStream_t st) {
-    auto kern = cov_mma_kernel<NB, KS_T, KERNEL, GRAD, ZI, MULTI, TWO>;
+    auto kern = cov_mma_kernel<NB, KS_T, KERNEL, GRAD, ZI, MULTI, TWO, BIG>;
     static bool configured[MAX_DEV] = {};
     int dev = 0;
     { int rc = current_device(&dev); if (rc) return rc; }
     if (!configured[dev]) {
-        GPRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_smem_bytes(NB, GPRB_MAX_KS, GRAD)));
+        GPRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)cov_smem_bytes(NB, BIG ? 2 * GPRB_MAX_KS : GPRB_MAX_KS, GRAD, BIG)));
         configured[dev] = true;
     }
     dim3 grid(n_blocks, P.n_splits);
-    kern<<<grid, THREADS, cov_smem_bytes(NB, P.ks, GRAD), st>>>(P);
+    kern<<<grid, BIG ? BIG_WARPS * 32 : THREADS, cov_smem_bytes(NB, P.ks, GRAD, BIG), st>>>(P);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
 }
 
 // the single-destination kernels carry no peer-store code at all (MULTI = false)
-template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI>
+template <int NB, int KS_T, int KERNEL, bool GRAD, int ZI, bool BIG = false>
 int launch_cov(const CovParams &P, int n_blocks, cudaStream_t st) {
+    if constexpr (BIG)
+        return P.n_extra > 0 ? launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, true, false, true>(P, n_blocks, st)
+                             : launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, false, false, true>(P, n_blocks, st);
     if constexpr (NB == 4 && KS_T == 8 && !GRAD) {
         if (P.two_stage)
             return P.n_extra > 0 ? launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, true, true>(P, n_blocks, st)
@@ -709,16 +719,17 @@ int launch_cov(const CovParams &P, int n_blocks, cudaStream_t st) {
                          : launch_cov_m<NB, KS_T, KERNEL, GRAD, ZI, false>(P, n_blocks, st);
 }
 
-template <int NB, int KS_T, int ZI>
+template <int NB, int KS_T, int ZI, bool BIG = false>
 int dispatch_kernel(int kernel, bool grad, const CovParams &P, int n_blocks, cudaStream_t st) {
-    if (kernel == GPRB_KERNEL_RBF) return grad ? launch_cov<NB, KS_T, GPRB_KERNEL_RBF, true, ZI>(P, n_blocks, st)
-                                               : launch_cov<NB, KS_T, GPRB_KERNEL_RBF, false, ZI>(P, n_blocks, st);
-    return launch_cov<NB, KS_T, GPRB_KERNEL_DOT, false, ZI>(P, n_blocks, st);
+    if (kernel == GPRB_KERNEL_RBF) return grad ? launch_cov<NB, KS_T, GPRB_KERNEL_RBF, true, ZI, BIG>(P, n_blocks, st)
+                                               : launch_cov<NB, KS_T, GPRB_KERNEL_RBF, false, ZI, BIG>(P, n_blocks, st);
+    return launch_cov<NB, KS_T, GPRB_KERNEL_DOT, false, ZI, BIG>(P, n_blocks, st);
 }
 
 template <int NB>
 int dispatch_cov(int kernel, bool grad, const CovParams &P, int n_blocks, cudaStream_t st) {
     const bool z2 = P.zi == 2;
+    if (P.ks > GPRB_MAX_KS) return dispatch_kernel<NB, 0, 0, true>(kernel, grad, P, n_blocks, st);     // d = 33..64
     if (P.ks == 8) return z2 ? dispatch_kernel<NB, 8, 2>(kernel, grad, P, n_blocks, st) : dispatch_kernel<NB, 8, 0>(kernel, grad, P, n_blocks, st);
     return z2 ? dispatch_kernel<NB, 0, 2>(kernel, grad, P, n_blocks, st) : dispatch_kernel<NB, 0, 0>(kernel, grad, P, n_blocks, st);
 }
@@ -777,8 +788,8 @@ static int kff_impl(int kernel, const gprb_pack *f1_, const gprb_pack *f2, doubl
     if (mode == GPRB_FF_SYMMETRIC)
         GPRB_REQUIRE(f1 == f2 && grp_begin == 0 && grp_end == f1->n_groups, "gprb_kff: symmetric mode needs f1 == f2 and the full window");
     if (mode == GPRB_FF_DIAG || mode == GPRB_FF_UPPER) GPRB_REQUIRE(f1 == f2, "gprb_kff: diag / upper mode needs f1 == f2");
-    if (f1->ks > GPRB_MAX_KS) {
-        gprb_set_error("gprb_kff: descriptor length %d > 32 is not supported by the DMMA kernels yet", f1->d);
+    if (f1->ks > 2 * GPRB_MAX_KS) {
+        gprb_set_error("gprb_kff: descriptor length %d > %d is not supported by the DMMA kernels", f1->d, 8 * GPRB_MAX_KS);
         return GPRB_ERR_UNSUPPORTED;
     }
     if (grp_begin == grp_end || f2->n_groups == 0) return GPRB_OK;
@@ -809,7 +820,7 @@ static int kff_impl(int kernel, const gprb_pack *f1_, const gprb_pack *f2, doubl
     // no-gradient K_ff with 8 k-steps (d = 29..32, the default descriptor): two-stage contraction, 1.44x the 4x4-block path
     // (profiles/r02_two_stage.txt); GPRB_KFF_TWO_STAGE=0 selects the block path for the A/B parity test
     const char *two_env = getenv("GPRB_KFF_TWO_STAGE");
-    P.two_stage = (!dK && mode != GPRB_FF_DIAG && !(two_env && two_env[0] == '0')) ? 1 : 0;
+    P.two_stage = (!dK && mode != GPRB_FF_DIAG && f1->ks == GPRB_MAX_KS && !(two_env && two_env[0] == '0')) ? 1 : 0;
     P.n_splits = mode == GPRB_FF_DIAG ? 1 : choose_splits(f1->sched_n, f2->n_groups);
     return dispatch_cov<4>(kernel, dK != nullptr, P, f1->sched_n, st);
 }
@@ -846,8 +857,8 @@ static int kef_impl(int kernel, const gprb_pack *e, const gprb_pack *f_, double 
     GPRB_REQUIRE(0 <= grp_begin && grp_begin <= grp_end && grp_end <= f->n_groups, "gprb_kef: bad window [%d,%d)", grp_begin, grp_end);
     const bool grad = dKef || dKfe;
     GPRB_REQUIRE(!(grad && kernel == GPRB_KERNEL_DOT), "gprb_kef: Dot has no dK output (closed form, see header)");
-    if (f->ks > GPRB_MAX_KS) {
-        gprb_set_error("gprb_kef: descriptor length %d > 32 is not supported by the DMMA kernels yet", f->d);
+    if (f->ks > 2 * GPRB_MAX_KS) {
+        gprb_set_error("gprb_kef: descriptor length %d > %d is not supported by the DMMA kernels", f->d, 8 * GPRB_MAX_KS);
         return GPRB_ERR_UNSUPPORTED;
     }
     if (grp_begin == grp_end || e->n_groups == 0) return GPRB_OK;
@@ -898,7 +909,7 @@ extern "C" int gprb_kfe_multi(int kernel, const gprb_pack *e, const gprb_pack *f
 // K_ee on the same tile machinery (NB = 0: one component per side, 8 DMMAs per 8 x 8 pairs, table exp, tiles without a
 // same-species pair skipped).  Replaces rbf_kee_many / rbf_kee_many_with_grad (rbf_kernel.cpp:5-98) and dot_kee_many
 // (dot_kernel.cpp:5-56) with the wrappers' 1 / (n_I n_J) (rbf_kernel.py:56-70, dot_kernel.py:46).  Descriptors longer than
-// 32 take the scalar kernel of cov_ee.cu.
+// 64 take the scalar kernel of cov_ee.cu.
 int gprb_kee_scalar(int kernel, const gprb_pack *e1, const gprb_pack *e2, double p0, double p1, double zeta,
                     int grp_begin, int grp_end, double *K, long long ldk, double *dK, long long lddk, cudaStream_t st);
 
@@ -914,7 +925,7 @@ extern "C" int gprb_kee(int kernel, const gprb_pack *e1_, const gprb_pack *e2, d
     GPRB_REQUIRE(0 <= grp_begin && grp_begin <= grp_end && grp_end <= e1->n_groups, "gprb_kee: bad window [%d,%d)", grp_begin, grp_end);
     GPRB_REQUIRE(!(dK && kernel == GPRB_KERNEL_DOT), "gprb_kee: Dot has no dK output (closed form, see header)");
     if (grp_begin == grp_end || e2->n_groups == 0) return GPRB_OK;
-    if (e1->ks > GPRB_MAX_KS || getenv("GPRB_KEE_SCALAR") != nullptr)      // env: A/B switch of the parity tests
+    if (e1->ks > 2 * GPRB_MAX_KS || getenv("GPRB_KEE_SCALAR") != nullptr)  // d > 64; env: A/B switch of the parity tests
         return gprb_kee_scalar(kernel, e1, e2, p0, p1, zeta, grp_begin, grp_end, K, ldk, dK, lddk, st);
     int rc = build_sched(e1, grp_begin, grp_end, st);
     if (rc) return rc;

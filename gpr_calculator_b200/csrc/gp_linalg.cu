@@ -569,23 +569,74 @@ extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const doub
     return GPRB_OK;
 }
 
+// one CTA per test row, half-product variant: W = Ks . triu(Kinv) (trmm), k^T Kinv k = sum_j k_j (2 W_j - Kinv_jj k_j)
+__global__ void __launch_bounds__(256) predict_rows_sym_kernel(int N, const double *__restrict__ Ks, long long ldks,
+                                                               const double *__restrict__ alpha, const double *__restrict__ W,
+                                                               const double *__restrict__ kdiag, const double *__restrict__ diag,
+                                                               double *mean, double *var) {
+    __shared__ double sh[32];
+    const int i = blockIdx.x;
+    const double *k = Ks + (long long)i * ldks;
+    const double *w = W + (long long)i * N;
+    double m = 0.0, v = 0.0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const double kj = k[j];
+        m = fma(kj, alpha[j], m);
+        v = fma(kj, fma(2.0, w[j], -kdiag[j] * kj), v);
+    }
+    m = block_sum(m, sh);
+    v = block_sum(v, sh);
+    if (threadIdx.x == 0) {
+        mean[i] = m;
+        const double r = diag[i] - v;
+        var[i] = r < 0.0 ? 0.0 : r;                  // gaussianprocess.py:906-907
+    }
+}
+
+__global__ void extract_diag_kernel(const double *A, long long ld, int N, double *d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) d[i] = A[(long long)i * ld + i];
+}
+
 extern "C" int gprb_predict(int m, int N, const double *Ks, long long ldks, const double *alpha,
                             const double *Kinv, long long ldi, const double *diag,
                             double *mean, double *var, double *work, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(Ks && alpha && mean && m >= 0 && N > 0, "gprb_predict: bad argument");
     if (m == 0) return GPRB_OK;
-    if (var) {
-        GPRB_REQUIRE(Kinv && diag && work, "gprb_predict: variance needs Kinv, diag and work");
-        int rc = handles(st);
-        if (rc) return rc;
-        // row-major work[m,N] = Ks[m,N] . Kinv[N,N]  ==  column-major work^T = Kinv^T . Ks^T
-        const double one = 1.0, zero = 0.0;
-        cublasStatus_t bs = cublasDgemm(g_blas, CUBLAS_OP_N, CUBLAS_OP_N, N, m, N, &one, Kinv, (int)ldi, Ks, (int)ldks,
-                                        &zero, work, N);
-        if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDgemm status %d", (int)bs); return GPRB_ERR_CUDA; }
+    if (!var) {
+        predict_rows_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, nullptr, diag, mean, var);
+        GPRB_LAUNCHED();
+        GPRB_CUDA(cudaGetLastError());
+        return GPRB_OK;
     }
-    predict_rows_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, var ? work : nullptr, diag, mean, var);
+    GPRB_REQUIRE(Kinv && diag && work, "gprb_predict: variance needs Kinv, diag and work");
+    int rc = handles(st);
+    if (rc) return rc;
+    const double one = 1.0, zero = 0.0;
+    if (getenv("GPRB_PREDICT_TRMM") != nullptr) {
+        // K^-1 is symmetric: work = Ks . triu(Kinv) is half the flops of the full product (m N^2 instead of 2 m N^2);
+        // column-major view: work^T (N x m) = A . Ks^T with A = the triangle of Kinv that holds the row-major upper part
+        Scratch scratch(st);
+        double *kd = (double *)scratch.get((size_t)N * sizeof(double));
+        if (!kd) return GPRB_ERR_CUDA;
+        extract_diag_kernel<<<(N + 255) / 256, 256, 0, st>>>(Kinv, ldi, N, kd);
+        GPRB_LAUNCHED();
+        // row-major upper triangle of Kinv == column-major LOWER triangle; (A Ks^T)[i, r] = sum_{j <= i (cm)} ...: by symmetry
+        // either triangle gives the same half-sum as long as the diagonal correction above is applied
+        cublasStatus_t bs = cublasDtrmm(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+                                        N, m, &one, Kinv, (int)ldi, Ks, (int)ldks, work, N);
+        if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDtrmm status %d", (int)bs); return GPRB_ERR_CUDA; }
+        predict_rows_sym_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, work, kd, diag, mean, var);
+        GPRB_LAUNCHED();
+        GPRB_CUDA(cudaGetLastError());
+        return GPRB_OK;
+    }
+    // row-major work[m,N] = Ks[m,N] . Kinv[N,N]  ==  column-major work^T = Kinv^T . Ks^T
+    cublasStatus_t bs = cublasDgemm(g_blas, CUBLAS_OP_N, CUBLAS_OP_N, N, m, N, &one, Kinv, (int)ldi, Ks, (int)ldks,
+                                    &zero, work, N);
+    if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDgemm status %d", (int)bs); return GPRB_ERR_CUDA; }
+    predict_rows_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, work, diag, mean, var);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;

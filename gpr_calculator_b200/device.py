@@ -13,6 +13,7 @@ from . import _lib
 from ._lib import c_vp, c_int
 
 F64 = torch.float64
+MAX_DESCRIPTOR = 64         # 16 k-steps of the DMMA kernels (csrc/cov_mma.cu)
 
 
 def require_cuda():
@@ -70,6 +71,9 @@ class Pack:
                 raise ValueError("ele has %d entries for %d rows" % (len(ele), n_rows))
             if dxdr is not None and tuple(dxdr.shape) != (n_rows, d, 3):
                 raise ValueError("dxdr must have shape (%d, %d, 3), got %s" % (n_rows, d, tuple(dxdr.shape)))
+        if d > MAX_DESCRIPTOR:      # fail before the rows are packed, not at the first covariance build
+            raise _lib.GprB200Error(_lib.ERR_UNSUPPORTED, "descriptor length %d > %d is not supported by the device kernels "
+                                    "(e.g. SO3 needs nmax (nmax + 1) / 2 * (lmax + 1) <= %d)" % (d, MAX_DESCRIPTOR, MAX_DESCRIPTOR))
         self.ncols = 0 if dxdr is None else 3
         self.n_groups = len(rows)
         self.n_rows = n_rows
@@ -110,19 +114,25 @@ def _root(a):
     return a
 
 
-def _cached(key_arr, n_groups, build):
-    if not isinstance(key_arr, np.ndarray) or key_arr.size == 0:
+def _cached(kind, arrays, indices, build):
+    """Pack of a packed tuple of host arrays, built once per (kind, identity of EVERY array, group sizes).
+
+    The key carries the pack kind (an array used as energy data and as force data gives two packs), address / shape /
+    strides of all arrays and the group sizes; an entry lives as long as all its arrays do.  Arrays mutated IN PLACE are not
+    detected (GP replaces its training arrays on every change, gaussianprocess.py:579-629); call clear_cache() after
+    doing so."""
+    if not all(isinstance(a, np.ndarray) for a in arrays) or arrays[0].size == 0:
         return build()
-    key = (key_arr.__array_interface__["data"][0], key_arr.shape, n_groups)
+    key = (kind,) + tuple((a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str) for a in arrays) + \
+        (tuple(int(v) for v in indices),)
     hit = _CACHE.get(key)
-    if hit is not None and hit[0]() is not None:
+    if hit is not None and all(r() is not None for r in hit[0]):
         return hit[1]
-    root = _root(key_arr)
     pack = build()
-    for k in [k for k, v in _CACHE.items() if v[0]() is None]:
+    for k in [k for k, v in _CACHE.items() if any(r() is None for r in v[0])]:
         del _CACHE[k]
     try:
-        _CACHE[key] = (weakref.ref(root), pack)
+        _CACHE[key] = ([weakref.ref(_root(a)) for a in arrays], pack)
     except TypeError:
         pass
     return pack
@@ -142,7 +152,7 @@ def energy_pack(data):
         X, ELE, indices = data
         if len(indices) == 0:
             return None
-        return _cached(X, len(indices), lambda: Pack(X, ELE, indices))
+        return _cached("energy", (X, ELE), indices, lambda: Pack(X, ELE, indices))
     if len(data) == 0:
         return None
     from .utilities import list_to_tuple
@@ -161,7 +171,7 @@ def force_pack(data, norm_eps=0.0):
         if len(indices) == 0:
             return None
         build = lambda: Pack(X, ELE, indices, dxdr=dXdR[:, :, :3] if dXdR.shape[2] != 3 else dXdR, norm_eps=norm_eps)  # noqa: E731
-        return build() if norm_eps else _cached(X, len(indices), build)
+        return build() if norm_eps else _cached("force", (X, dXdR, ELE), indices, build)
     if len(data) == 0:
         return None
     from .utilities import list_to_tuple

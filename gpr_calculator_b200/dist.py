@@ -14,6 +14,7 @@ copies, and two stream-ordered rank barriers replace the all-gather.
 import ctypes
 import os
 import warnings
+import weakref
 
 import numpy as np
 import torch
@@ -215,53 +216,73 @@ class PeerMatrix:
         from . import _lib
         rank, size = world()
         self.N, self.rank, self.size, self.group = int(N), rank, size, group
-        self.ptrs, self._opened, self._local = [], [], ctypes.c_void_p(0)
+        self.ptrs, self._opened, self._local, self.tensor = [], [], ctypes.c_void_p(0), None
         nbytes = self.N * self.N * 8
-        _lib.call("gprb_peer_alloc", ctypes.byref(self._local), ctypes.c_ulonglong(nbytes))
-        try:
-            handle = ctypes.create_string_buffer(64)
-            _lib.call("gprb_peer_export", self._local, handle)
-            mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda()
-            every = torch.empty(size * 64, dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(every, mine, group=group)
-            every = bytes(every.cpu().numpy().tobytes())
-            ok, err = 1, ""
-            ptrs = []
-            for r in range(size):
-                if r == rank:
-                    ptrs.append(int(self._local.value))
-                    continue
-                q = ctypes.c_void_p(0)
-                try:
-                    _lib.call("gprb_peer_open", every[64 * r:64 * (r + 1)], ctypes.byref(q))
-                    self._opened.append(q)
-                    ptrs.append(int(q.value))
-                except _lib.GprB200Error as exc:      # no peer access to that GPU (not one NVLink node?)
-                    ok, err = 0, str(exc)
-                    ptrs.append(0)
-            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+
+        def agreed(ok):
+            """Collective: True only if every rank succeeded so far (every rank takes part in every collective of the
+            constructor, whatever happened locally, so a local failure can never leave the others waiting)."""
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if int(flag.item()) == 0:
-                raise RuntimeError("peer mapping of K failed on at least one rank %s" % err)
-        except Exception:
+            return int(flag.item()) == 1
+
+        handle = ctypes.create_string_buffer(64)
+        err = ""
+        try:       # a second N x N buffer: may fail on a full device, on this rank only
+            _lib.call("gprb_peer_alloc", ctypes.byref(self._local), ctypes.c_ulonglong(nbytes))
+            _lib.call("gprb_peer_export", self._local, handle)
+            ok = True
+        except _lib.GprB200Error as exc:
+            ok, err = False, str(exc)
+        if not agreed(ok):
             self._release()
-            raise
+            raise RuntimeError("peer allocation of K failed on at least one rank %s" % err)
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda()
+        every = torch.empty(size * 64, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(every, mine, group=group)
+        every = bytes(every.cpu().numpy().tobytes())
+        ptrs = []
+        for r in range(size):
+            if r == rank:
+                ptrs.append(int(self._local.value))
+                continue
+            q = ctypes.c_void_p(0)
+            try:
+                _lib.call("gprb_peer_open", every[64 * r:64 * (r + 1)], ctypes.byref(q))
+                self._opened.append(q)
+                ptrs.append(int(q.value))
+            except _lib.GprB200Error as exc:      # no peer access to that GPU (not one NVLink node?)
+                ok, err = False, str(exc)
+                ptrs.append(0)
+        if not agreed(ok):
+            self._release()
+            raise RuntimeError("peer mapping of K failed on at least one rank %s" % err)
         self.ptrs = ptrs
         self.tensor = torch.as_tensor(_RawDeviceArray(self._local.value, (self.N, self.N)), device="cuda")
         self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
+        # best effort when a GP is dropped without release_peer(): unmap the peers and free the local buffer (not collective;
+        # a peer that still stores into this copy is a caller error, as with close())
+        self._finalizer = weakref.finalize(self, PeerMatrix._free, self._opened, self._local)
+
+    @staticmethod
+    def _free(opened, local):
+        try:
+            from . import _lib
+            lib = _lib.load()
+            for q in opened:
+                lib.gprb_peer_close(q)
+            del opened[:]
+            if local:
+                lib.gprb_peer_free(local)
+                local.value = None
+        except Exception:
+            pass
 
     def barrier(self):
         dist.all_reduce(self._token, group=self.group)
 
     def _release(self):
-        from . import _lib
-        lib = _lib.load()
-        for q in self._opened:
-            lib.gprb_peer_close(q)
-        self._opened = []
-        if self._local:
-            lib.gprb_peer_free(self._local)
-            self._local = ctypes.c_void_p(0)
+        PeerMatrix._free(self._opened, self._local)
         self.ptrs = []
 
     def close(self):
@@ -270,10 +291,10 @@ class PeerMatrix:
             self.barrier()
             torch.cuda.synchronize()
             self.tensor = None
+            from . import _lib
             for q in self._opened:          # unmap the peers' copies first, then everyone frees its own
-                from . import _lib
                 _lib.load().gprb_peer_close(q)
-            self._opened = []
+            del self._opened[:]
             self.barrier()
             torch.cuda.synchronize()
             self._release()
@@ -288,6 +309,6 @@ def make_peer_matrix(N, group=None):
     """PeerMatrix or None (with a warning) when the ranks cannot map each other's memory."""
     try:
         return PeerMatrix(N, group=group)
-    except Exception as exc:      # same outcome on every rank (the success flag is all-reduced)
+    except RuntimeError as exc:      # same outcome on every rank (every step's success flag is all-reduced)
         warnings.warn("fused peer gather unavailable, using the NCCL all-gather: %s" % exc)
         return None

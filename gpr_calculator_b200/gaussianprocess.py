@@ -1163,6 +1163,11 @@ class GP():
         else:
             raise NotImplementedError("unknown descriptors {:s}".format(str(dict0["descriptor"].get("name"))))
 
+        from .device import MAX_DESCRIPTOR
+        n_, l_ = instance.descriptor.nmax, instance.descriptor.lmax
+        if n_ * (n_ + 1) // 2 * (l_ + 1) > MAX_DESCRIPTOR:      # before every descriptor of the database is recomputed
+            raise NotImplementedError("SO3(nmax=%d, lmax=%d) gives descriptors of %d entries; the device kernels support %d"
+                                      % (n_, l_, n_ * (n_ + 1) // 2 * (l_ + 1), MAX_DESCRIPTOR))
         if "base_potential" in dict0.keys():
             raise NotImplementedError("base potentials are outside the B200 hot path (SURVEY.md §2.1 #13)")
         instance.kernel.device = device

@@ -363,7 +363,8 @@ def test_sigma_routes_against_reference_formula(monkeypatch, capsys):
     E_dev, F_dev = syn.packed_from_batch(des, [a for a, _, _ in labelled])
     gp = GP(kernel=RBF_mb(para=[1.0, 0.1], zeta=2.0), descriptor=des, noise_e=0.002, noise_f=0.1, log_file=None)
     gp.train_x = {"energy": gdev.Pack(E_dev[0], E_dev[1], E_dev[2]), "force": gdev.Pack(F_dev[0], F_dev[2], F_dev[3], dxdr=F_dev[1])}
-    gp.y_train = syn.targets(labelled)
+    y = syn.targets(labelled)
+    gp.train_y = {"energy": list(y[:24, 0]), "force": y[24:, 0].reshape(-1, 3)}
     gp.N_energy, gp.N_forces = 24, 24 * 32
     gp.fit(opt=False, show=False)
     tests_ = [a for a, _, _ in syn.structures(20, 2, 3000)]          # 20 x 97 = 1 940 rows of K*: the batch routes apply

@@ -98,6 +98,10 @@ CASES = [
     ("d7", dict(n_groups=5, lo=5, hi=20, d=7), dict(n_groups=4, lo=5, hi=20, d=7)),
     ("d32", dict(n_groups=4, lo=5, hi=20, d=32), dict(n_groups=4, lo=5, hi=20, d=32)),
     ("big_norms", dict(n_groups=5, lo=20, hi=35, scale=7e3), dict(n_groups=5, lo=20, hi=35, scale=7e3)),
+    # descriptors of 33..64 entries (e.g. SO3(nmax=4, lmax=4): d = 50) take the 6-warp / 16-k-step instantiations
+    ("d40", dict(n_groups=7, lo=5, hi=30, d=40), dict(n_groups=5, lo=5, hi=30, d=40)),
+    ("d50", dict(n_groups=9, lo=3, hi=60, d=50, species=(1, 16, 46)), dict(n_groups=6, lo=3, hi=60, d=50, species=(1, 16, 46))),
+    ("d64", dict(n_groups=4, lo=40, hi=70, d=64), dict(n_groups=5, lo=1, hi=20, d=64)),
 ]
 
 
@@ -136,12 +140,12 @@ def test_disjoint_species_give_zero():
     assert np.count_nonzero(rk.kff_C(F1, F2, 1.0, 0.5, 2.0)) == 0
 
 
-def test_descriptor_longer_than_32_fails_loudly():
+def test_descriptor_longer_than_64_fails_loudly():
     from gpr_calculator_b200 import _lib
     from gpr_calculator_b200.kernels import rbf_kernel as rk
     from gpr_calculator_b200.utilities import list_to_tuple
     rng = np.random.default_rng(6)
-    F = list_to_tuple(make_force(rng, 2, d=40))
+    F = list_to_tuple(make_force(rng, 2, d=72))
     with pytest.raises(_lib.GprB200Error):
         rk.kff_C(F, F, 1.0, 0.5, 2.0)
 

@@ -30,8 +30,11 @@ for m in (97, 291, 582, 1067, 2037, 3104):
     Ks = rows[:m].contiguous()
     diag = torch.full((m,), 1e3, dtype=torch.float64, device="cuda")
     res = {}
-    for route in ("inverse", "chol"):
-        os.environ["GPRB_VARIANCE_ROUTE"] = route
+    for route in ("inverse", "trmm", "chol"):
+        os.environ["GPRB_VARIANCE_ROUTE"] = "inverse" if route == "trmm" else route
+        os.environ.pop("GPRB_PREDICT_TRMM", None)
+        if route == "trmm":
+            os.environ["GPRB_PREDICT_TRMM"] = "1"
         for _ in range(2):
             mean, var = gp._mean_var(Ks, diag)
         torch.cuda.synchronize()
@@ -43,5 +46,6 @@ for m in (97, 291, 582, 1067, 2037, 3104):
         torch.cuda.synchronize()
         res[route] = (e0.elapsed_time(e1) / 5, var.cpu().numpy())
     d = np.abs(res["inverse"][1] - res["chol"][1]).max() / np.abs(1e3 - res["inverse"][1]).max()
-    print("m=%5d N=%d  inverse (gemm) %.2f ms   chol (trsm) %.2f ms   max rel diff of k*^T K^-1 k* %.2e"
-          % (m, N, res["inverse"][0], res["chol"][0], d), flush=True)
+    d2 = np.abs(res["inverse"][1] - res["trmm"][1]).max() / np.abs(1e3 - res["inverse"][1]).max()
+    print("m=%5d N=%d  inverse (gemm) %.2f ms   inverse, half product (trmm) %.2f ms   chol (trsm) %.2f ms   max rel diff of "
+          "k*^T K^-1 k*: chol %.2e, trmm %.2e" % (m, N, res["inverse"][0], res["trmm"][0], res["chol"][0], d, d2), flush=True)
