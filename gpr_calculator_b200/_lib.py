@@ -59,6 +59,8 @@ SIGNATURES = {
                              c_vp, c_vp, c_vp]),
     "gprb_predict": (c_int, [c_int, c_int, c_vp, c_ll, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gprb_predict_chol": (c_int, [c_int, c_int, c_vp, c_ll, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gprb_predict_cov": (c_int, [c_int, c_int, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp]),
+    "gprb_cur_scores": (c_int, [c_vp, c_ll, c_int, c_dbl, c_vp, c_vp, c_int_p, c_vp]),
     "gprb_so3_neighbors": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gprb_so3_radial": (c_int, [c_int, c_vp, c_int, c_int, c_int, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp]),
     "gprb_so3_power": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_dbl, c_dbl, c_vp,

@@ -683,6 +683,72 @@ extern "C" int gprb_predict_chol(int m, int N, const double *Ks, long long ldks,
     return GPRB_OK;
 }
 
+// y_cov = Kxx - K* K^-1 K*^T through the factor, the way gaussianprocess.py:363-366 does it (cho_solve):
+// Y = L^-1 K*^T (one trsm with m right-hand sides), cov -= Y^T Y.  cov_dev holds k(X, X) on entry.
+extern "C" int gprb_predict_cov(int m, int N, const double *Ks, long long ldks, const double *L, long long ldl,
+                                double *cov, long long ldc, double *work, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(Ks && L && cov && work && m >= 0 && N > 0 && ldc >= m, "gprb_predict_cov: bad argument");
+    if (m == 0) return GPRB_OK;
+    int rc = handles(st);
+    if (rc) return rc;
+    GPRB_CUDA(cudaMemcpy2DAsync(work, (size_t)N * sizeof(double), Ks, (size_t)ldks * sizeof(double), (size_t)N * sizeof(double), m,
+                                cudaMemcpyDeviceToDevice, st));
+    const double one = 1.0, minus = -1.0;
+    cublasStatus_t bs = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, FACTOR_UPLO, solve_op(0), CUBLAS_DIAG_NON_UNIT,
+                                       (int64_t)N, (int64_t)m, &one, L, (int64_t)ldl, work, (int64_t)N);
+    if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDtrsm_64 (predict_cov) status %d", (int)bs); return GPRB_ERR_CUDA; }
+    // column-major view: work is Y (N x m); cov (m x m, symmetric) -= Y^T Y
+    bs = cublasDgemm(g_blas, CUBLAS_OP_T, CUBLAS_OP_N, m, m, N, &minus, work, N, work, N, &one, cov, (int)ldc);
+    if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDgemm (predict_cov) status %d", (int)bs); return GPRB_ERR_CUDA; }
+    return GPRB_OK;
+}
+
+namespace {
+// omega[i] = sum over the first n_low eigenvectors (rows of V, ascending eigenvalues) of V[k][i]^2
+__global__ void leverage_kernel(const double *V, long long ld, int n, int n_low, double *omega) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (int k = 0; k < n_low; k++) { const double v = V[(long long)k * ld + i]; acc = fma(v, v, acc); }
+    omega[i] = acc;
+}
+}  // namespace
+
+// CUR leverage scores (gaussianprocess.py:1165-1182): eigen-decomposition of the symmetric block A (cuSOLVER syevd, in
+// place: on return row k of A is the eigenvector of the k-th smallest eigenvalue), eigenvalues to w_host[n],
+// omega_dev[i] = sum_{k: w_k < l_tol} U[i, k]^2; *n_low_host = number of eigenvalues below l_tol.
+extern "C" int gprb_cur_scores(double *A, long long lda, int n, double l_tol, double *w_host, double *omega, int *n_low_host,
+                               void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(A && w_host && omega && n_low_host && n > 0 && lda >= n, "gprb_cur_scores: bad argument");
+    int rc = handles(st);
+    if (rc) return rc;
+    Scratch scratch(st);
+    double *w = (double *)scratch.get((size_t)n * sizeof(double));
+    int *info = (int *)scratch.get(sizeof(int));
+    if (!w || !info) return GPRB_ERR_CUDA;
+    int lwork = 0;
+    if (cusolverDnDsyevd_bufferSize(g_solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, (int)lda, w, &lwork) !=
+        CUSOLVER_STATUS_SUCCESS) { gprb_set_error("syevd_bufferSize failed"); return GPRB_ERR_CUDA; }
+    double *work = (double *)scratch.get((size_t)(lwork > 0 ? lwork : 1) * sizeof(double));
+    if (!work) return GPRB_ERR_CUDA;
+    cusolverStatus_t cs = cusolverDnDsyevd(g_solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, A, (int)lda, w, work, lwork, info);
+    if (cs != CUSOLVER_STATUS_SUCCESS) { gprb_set_error("cusolverDnDsyevd status %d", (int)cs); return GPRB_ERR_CUDA; }
+    int hinfo = -1;
+    GPRB_CUDA(cudaMemcpyAsync(w_host, w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GPRB_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GPRB_CUDA(cudaStreamSynchronize(st));
+    if (hinfo != 0) { gprb_set_error("syevd did not converge (info = %d)", hinfo); return GPRB_ERR_LINALG; }
+    int n_low = 0;
+    while (n_low < n && w_host[n_low] < l_tol) n_low++;        // eigenvalues are ascending
+    *n_low_host = n_low;
+    leverage_kernel<<<(n + 255) / 256, 256, 0, st>>>(A, lda, n, n_low, omega);
+    GPRB_LAUNCHED();
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
 // dst[j][i] = src[i][j] for a rows x cols block (32 x 32 tiles through shared memory)
 __global__ void transpose_copy_kernel(double *dst, long long ldd, const double *src, long long lds, int rows, int cols) {
     __shared__ double t[32][33];

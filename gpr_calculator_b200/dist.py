@@ -145,6 +145,32 @@ def all_reduce_sum(values, device="cpu", group=None):
     return [float(v) for v in t.cpu()]
 
 
+def all_to_all_rows(out, inp, recv_rows, send_rows, group=None):
+    """Exchange contiguous row blocks of two row-major matrices with the same row length: this rank sends send_rows[d]
+    consecutive rows of `inp` to rank d (in rank order) and receives recv_rows[s] rows from rank s into `out`
+    (in rank order).  Point-to-point sends / receives in one batch (NCCL: one grouped launch over NVLink; gloo in the tests);
+    the rank's own block is a local copy."""
+    rank, size = world()
+    assert out.shape[1] == inp.shape[1] and sum(send_rows) == inp.shape[0] and sum(recv_rows) == out.shape[0]
+    so = np.concatenate(([0], np.cumsum(send_rows))).astype(int)
+    ro = np.concatenate(([0], np.cumsum(recv_rows))).astype(int)
+    ops = []
+    for p in range(size):
+        peer = p if group is None else dist.get_global_rank(group, p)
+        if p == rank:
+            if send_rows[p]:
+                out[ro[p]:ro[p + 1]] = inp[so[p]:so[p + 1]]
+            continue
+        if send_rows[p]:
+            ops.append(dist.P2POp(dist.isend, inp[so[p]:so[p + 1]], peer, group=group))
+        if recv_rows[p]:
+            ops.append(dist.P2POp(dist.irecv, out[ro[p]:ro[p + 1]], peer, group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out
+
+
 def all_reduce_array(values, device="cpu", group=None):
     """Element-wise sum of a 1-D float64 numpy array over ranks (sharded prediction: every rank fills its own slots of a
     zero array, so the sum is an exact gather)."""

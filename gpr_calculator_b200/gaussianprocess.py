@@ -360,6 +360,8 @@ class GP():
         N = K.shape[0]
         NE = self._n_energy_rows()
         full_inverse = os.environ.get("GPRB_FULL_INVERSE", "0") not in ("", "0")
+        if eval_gradient and is_rbf and not full_inverse and gdist.world()[1] > 1:
+            dK, r_ranges = self._rebalance_dK(dK, r_ranges, N, NE)
         try:
             alpha, out = self._lml_eval(K, dK if is_rbf else None, r_ranges, noise_e, noise_f,
                                         want_grad=eval_gradient and not full_inverse, want_s0=not is_rbf)
@@ -385,6 +387,36 @@ class GP():
         if self.noise_bounds is None:
             llg = llg[:-1]
         return self._sync_ranks(MLL, llg)
+
+    def _rebalance_dK(self, dK, r_ranges, N, NE):
+        """Re-cut the force rows of dK/dl over the ranks for the inverse-rows likelihood gradient.
+
+        The covariance build balances n_I * sum_{J >= I} n_J (cost of the K_ff rows, ~ (N - r) per row); the trailing-block
+        solves that follow cost (N - r)^2 per row, so the build's windows leave the first ranks with about twice the
+        ideal solve time (SCALE_r01: 221 ms on rank 0 at 8 GPUs against 124 ms ideal).  dK/dl is only consumed by the
+        traces, so its force rows are exchanged (one all-to-all over NVLink, about a third of the slab) into windows
+        balanced for the solves; K is untouched.  GPRB_BALANCE_INVERSE=0 keeps the build's windows."""
+        rank, size = gdist.world()
+        if os.environ.get("GPRB_BALANCE_INVERSE", "1") in ("", "0") or dK is None or len(r_ranges) != 2:
+            return dK, r_ranges
+        (e0, e1), (r0, r1) = r_ranges
+        NF = (N - NE) // 3
+        first = NE + 3 * np.arange(NF, dtype=np.float64)
+        bounds = gdist.split_groups(3.0 * (N - first) ** 2, size)
+        f_old = gdist.all_gather_floats(float((r0 - NE) // 3), device="cuda") + [float(NF)]
+        f_old = [int(v) for v in f_old]                      # force windows of the build, by rank (contiguous, ordered)
+        # sanity: the build's windows tile [0, NF)
+        if f_old[0] != 0 or any(f_old[k] > f_old[k + 1] for k in range(size)) or (r1 - NE) // 3 != f_old[rank + 1]:
+            return dK, r_ranges
+        ne_loc = e1 - e0
+        send = [3 * max(0, min(f_old[rank + 1], bounds[d + 1]) - max(f_old[rank], bounds[d])) for d in range(size)]
+        recv = [3 * max(0, min(f_old[s_ + 1], bounds[rank + 1]) - max(f_old[s_], bounds[rank])) for s_ in range(size)]
+        g0, g1 = bounds[rank], bounds[rank + 1]
+        new = torch.empty((ne_loc + 3 * (g1 - g0), N), dtype=F64, device="cuda")
+        if ne_loc:
+            new[:ne_loc] = dK[:ne_loc]
+        gdist.all_to_all_rows(new[ne_loc:], dK[ne_loc:], recv, send)
+        return new, [(e0, e1), (NE + 3 * g0, NE + 3 * g1)]
 
     def _sync_ranks(self, lml, grad=None):
         """Every rank continues with rank 0's values (the reference broadcasts the parameters after each optimiser
@@ -599,8 +631,7 @@ class GP():
             # gaussianprocess.py:331-333: K* from k_total_with_stress, the stress rows themselves are discarded
             K_trans, _ = self.kernel.k_total_stress_device(X, train_x)
             return_std = return_cov = False
-            mean = K_trans @ self._alpha_dev
-            var = None
+            mean, var = self._mean_var(K_trans, None)
         else:
             K_trans, mean, var = self._predict_device(X, train_x, 1e-10, return_std and not return_cov)
         y_mean = mean.cpu().numpy()
@@ -620,10 +651,12 @@ class GP():
         y_mean *= factors
 
         if return_cov:
-            # y_cov = k(X, X) - K* K^-1 K*^T   (:363-366)
-            self.set_K_inv()
-            Kxx, _ = self.kernel.k_total_device(X, None, grad=False)
-            y_cov = Kxx - K_trans @ (self._Kinv_dev @ K_trans.T)
+            # y_cov = k(X, X) - K* K^-1 K*^T with v = cho_solve(L, K*^T)   (:363-366)
+            y_cov, _ = self.kernel.k_total_device(X, None, grad=False)
+            m_, N_ = K_trans.shape
+            work = torch.empty((m_, N_), dtype=F64, device="cuda")
+            _lib.call("gprb_predict_cov", m_, N_, ptr(K_trans), K_trans.stride(0), ptr(self._L_dev), N_, ptr(y_cov), y_cov.stride(0),
+                      ptr(work), stream())
             return y_mean, y_cov.cpu().numpy()
         elif return_std:
             return y_mean, np.sqrt(var.cpu().numpy()) * factors
@@ -953,7 +986,7 @@ class GP():
         F_all = y_mean[1:].reshape(n, 3)
         F = np.zeros((n, 3))
         F[free_ids] = F_all[free_ids]
-        S = (K1 @ self._alpha_dev).cpu().numpy().reshape(n, 6)
+        S = self._mean_var(K1, None)[0].cpu().numpy().reshape(n, 6)
         if self.base_potential is not None:
             energy_off, force_off, stress_off = self.compute_base_potential(struc)
             E += energy_off
@@ -1081,7 +1114,7 @@ class GP():
 
     def sparsify(self, e_tol=1e-10, f_tol=1e-10):
         """Drop training points in the near-null space of K (CUR, gaussianprocess.py:1004-1023).  K stays on
-        the device: eigen-decomposition by cuSOLVER syevd (torch.linalg.eigh), leverage scores there; the
+        the device: eigen-decomposition by cuSOLVER syevd and leverage scores in gprb_cur_scores; the
         O(N_f^2) Python double loop of the reference is a vectorised membership test."""
         require_cuda()
         K, _ = self.kernel.k_total_device(self.train_x, None, grad=False)
@@ -1182,16 +1215,19 @@ ctypes_double = ctypes.c_double
 
 
 def CUR_device(K, l_tol=1e-10):
-    """CUR on a device-resident block: same selection as CUR() below."""
-    if K.shape[0] == 0:
+    """CUR on a device-resident block: same selection as CUR() below (cuSOLVER syevd + leverage scores in
+    gprb_cur_scores; the block is copied because the decomposition works in place)."""
+    n = K.shape[0]
+    if n == 0:
         return np.zeros(0, dtype=np.int64)
-    L, U = torch.linalg.eigh(K)
-    low = L < l_tol
-    n_low = int(low.sum())
-    if n_low == 0:
+    A = K.clone().contiguous()
+    w = np.zeros(n)
+    omega = torch.empty(n, dtype=F64, device="cuda")
+    n_low = ctypes.c_int(0)
+    _lib.call("gprb_cur_scores", ptr(A), A.stride(0), n, float(l_tol), w.ctypes.data, ptr(omega), ctypes.byref(n_low), stream())
+    if n_low.value == 0:
         return np.zeros(0, dtype=np.int64)
-    omega = (U[:, low] ** 2).sum(dim=1)
-    return torch.argsort(-omega, stable=True)[:n_low].cpu().numpy()
+    return np.argsort(-1 * omega.cpu().numpy(), kind="stable")[:n_low.value]
 
 
 def CUR(K, l_tol=1e-10):

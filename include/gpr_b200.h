@@ -215,6 +215,17 @@ int gprb_predict_chol(int m, int N, const double *Ks_dev, long long ldks, const 
                       const double *L_dev, long long ldl, const double *diag_dev,
                       double *mean_dev, double *var_dev, double *work_dev, void *stream);
 
+/* cov_dev (m x m, holds k(X, X) on entry) -= K* K^-1 K*^T through the factor, as GP.predict(return_cov=True) does with
+ * cho_solve (gaussianprocess.py:363-366): one cuBLAS trsm with m right-hand sides + one m x m x N gemm.  work_dev: [m, N]. */
+int gprb_predict_cov(int m, int N, const double *Ks_dev, long long ldks, const double *L_dev, long long ldl,
+                     double *cov_dev, long long ldc, double *work_dev, void *stream);
+
+/* CUR leverage scores of a symmetric block (CUR(), gaussianprocess.py:1165-1182; Jinnouchi et al. PRB 100, 014105 App. D):
+ * cuSOLVER syevd in place (A_dev is destroyed: row k = eigenvector of the k-th smallest eigenvalue), eigenvalues to
+ * w_host[n], omega_dev[i] = sum_{k: w_k < l_tol} U[i,k]^2, *n_low_host = #{w_k < l_tol}. */
+int gprb_cur_scores(double *A_dev, long long lda, int n, double l_tol, double *w_host, double *omega_dev, int *n_low_host,
+                    void *stream);
+
 /* ---- SO(3) power-spectrum descriptor (gpr_calc/SO3.py:186-727), batched over structures --------
  * Atoms of all structures are concatenated; atom_ptr[S+1] gives the first atom of each structure,
  * struct_of[n_atoms] the structure of each atom.  All pointers are device pointers.

@@ -291,8 +291,14 @@ def install():
 
     rbf = ctypes.CDLL(os.path.join(here, "_ref", "librbf_ref.so"))
     dot = ctypes.CDLL(os.path.join(here, "_ref", "libdot_ref.so"))
-    sys.path.insert(0, REF_ROOT)
-    import gpr_calc  # namespace package rooted at the reference tree
+    # `gpr_calc` is seeded explicitly as a namespace rooted at the reference tree: the repository ships an import-path
+    # alias package of the same name (gpr_calc/__init__.py -> gpr_calculator_b200), and a regular package anywhere on
+    # sys.path would win over the reference's namespace package
+    for name in [n for n in sys.modules if n == "gpr_calc" or n.startswith("gpr_calc.")]:
+        del sys.modules[name]
+    pkg = types.ModuleType("gpr_calc")
+    pkg.__path__ = [os.path.join(REF_ROOT, "gpr_calc")]
+    sys.modules["gpr_calc"] = pkg
     import gpr_calc.kernels  # noqa: F401
     mod("gpr_calc.kernels._rbf_kernel", lib=_RefLib(rbf, _RBF_SIGS))
     mod("gpr_calc.kernels._dot_kernel", lib=_RefLib(dot, _DOT_SIGS))

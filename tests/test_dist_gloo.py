@@ -49,6 +49,14 @@ def _worker(rank, size, port, q):
             if std:
                 ok = ok and g[3] == t[3] and np.array_equal(g[4], t[4])
     ok = ok and gd.broadcast_floats([float(rank), 7.0], src=0) == [0.0, 7.0]
+    # re-cut of row slabs between two contiguous partitions (dK/dl rows for the inverse-rows gradient)
+    rows_all = torch.arange(13 * 4, dtype=torch.float64).reshape(13, 4)
+    old_b, new_b = [0, 9, 13], [0, 4, 13]
+    send = [max(0, min(old_b[rank + 1], new_b[d + 1]) - max(old_b[rank], new_b[d])) for d in range(size)]
+    recv = [max(0, min(old_b[s_ + 1], new_b[rank + 1]) - max(old_b[s_], new_b[rank])) for s_ in range(size)]
+    got_r = gd.all_to_all_rows(torch.empty((new_b[rank + 1] - new_b[rank], 4), dtype=torch.float64),
+                               rows_all[old_b[rank]:old_b[rank + 1]].clone(), recv, send)
+    ok = ok and bool(torch.equal(got_r, rows_all[new_b[rank]:new_b[rank + 1]]))
     s = gd.all_reduce_sum([float(rank + 1), 2.0])
     q.put((rank, ok, s, gd.world()))
     dist.destroy_process_group()

@@ -402,3 +402,80 @@ def test_sigma_routes_against_reference_formula(monkeypatch, capsys):
     assert d["device inverse route vs reference formula"] <= floor
     assert d["device chol route vs refined"] <= floor
     assert chosen in ("chol", "inverse") and (chosen == "chol") == (gp._variance_probe[2] <= 1e-8)
+
+
+@pytest.fixture(scope="module")
+def gsel():
+    return np.load(os.path.join(GOLD, "selection.npz"))
+
+
+def _fitted_b(g):
+    gp = _model(g)
+    gp.kernel.update([2.0, 0.8])
+    with contextlib.redirect_stdout(io.StringIO()):
+        gp.fit(opt=False, show=False)
+    return gp
+
+
+def test_add_structure_selection_vs_reference(g, gsel):
+    """GP.add_structure (gaussianprocess.py:921-1002) against the reference's own run on the same inputs: WHICH force
+    centres enter the training set and in what order (incl. the flat-F indexing of :979), the error tuple it returns,
+    the queue counters and the appended targets."""
+    new = _atoms(g, gsel["new_pos"], fixed=False)
+    E_new, F_new = float(gsel["new_E"]), gsel["new_F"]
+    cases = {"default": {}, "tight": {"tol_f_var": 0.05}, "capped": {"tol_f_var": 0.05, "N_max": 2}, "noforce": {"add_force": False}}
+    for tag, kw in cases.items():
+        gp = _fitted_b(g)
+        with contextlib.redirect_stdout(io.StringIO()):
+            pts, n_pts, err = gp.add_structure((new.copy(), E_new, F_new.copy()), **kw)
+        assert list(gp.train_db[-1][4]) == list(gsel[tag + "_force_in"]), tag
+        assert n_pts == int(gsel[tag + "_n_pts"])
+        assert [gp.N_energy, gp.N_forces, gp.N_energy_queue, gp.N_forces_queue, gp.N_queue] == list(gsel[tag + "_counters"])
+        assert np.abs(np.array([err[0], err[1]]) - gsel[tag + "_err_E"][:2]).max() <= 1e-8
+        assert np.abs(np.asarray(err[3]) - gsel[tag + "_err_F"]).max() <= 1e-8 and np.abs(np.asarray(err[4]) - gsel[tag + "_err_F1"]).max() <= 1e-8
+        assert abs(err[2] - gsel[tag + "_err_E"][2]) <= 1e-6 and np.abs(np.asarray(err[5]) - gsel[tag + "_err_Fstd"]).max() <= 1e-6
+        assert np.abs(gp.y_train - gsel[tag + "_y_train"]).max() <= 1e-12
+    # untrained model: every centre is a candidate, new_pt() removes near-duplicates
+    from gpr_calculator_b200.gaussianprocess import GP
+    from gpr_calculator_b200.kernels import RBF_mb
+    from gpr_calculator_b200.SO3 import SO3
+    gp = GP(kernel=RBF_mb(para=[2.0, 0.8], zeta=2.0), descriptor=SO3(nmax=3, lmax=4, rcut=5.0), noise_e=0.002, noise_f=0.1, log_file=None)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for k in range(3):
+            gp.add_structure((_atoms(g, g["t%d_pos" % k]), float(g["t%d_E" % k]), g["t%d_F" % k].copy()))
+            assert list(gp.train_db[-1][4]) == list(gsel["fresh%d_force_in" % k])
+    assert [gp.N_energy, gp.N_forces, gp.N_energy_queue, gp.N_forces_queue, gp.N_queue] == list(gsel["fresh_counters"])
+
+
+def test_predict_return_cov_vs_reference(g, gsel):
+    """GP.predict(X, return_cov=True) (gaussianprocess.py:363-366) on packed test data."""
+    from gpr_calculator_b200.SO3 import SO3
+    from gpr_calculator_b200.utilities import convert_train_data, list_to_tuple
+    gp = _fitted_b(g)
+    new = _atoms(g, gsel["new_pos"], fixed=False)
+    d = convert_train_data([(new, float(gsel["new_E"]), gsel["new_F"].copy())], SO3(nmax=3, lmax=4, rcut=5.0))
+    X = {"energy": list_to_tuple([(d["energy"][0][0], d["energy"][0][2])], mode="energy"),
+         "force": list_to_tuple([(f[0], f[1], f[3]) for f in d["force"][9:12]])}
+    y_mean, y_cov = gp.predict(X, return_cov=True)
+    assert np.abs(y_mean - gsel["cov_mean"]).max() <= 1e-8
+    assert y_cov.shape == gsel["cov_cov"].shape and np.abs(y_cov - gsel["cov_cov"]).max() <= 1e-7 * np.abs(gsel["cov_cov"]).max()
+
+
+def test_cur_selection_vs_reference(gsel):
+    """CUR (gaussianprocess.py:1165-1182) on covariance blocks with exactly duplicated training points: the number of
+    selected rows, the leverage scores (the projector diagonal onto the low eigen-space) and, where the scores are not tied,
+    the selected rows themselves, against the reference's own run."""
+    import torch
+    from gpr_calculator_b200.gaussianprocess import CUR_device
+    K, n_e = gsel["cur_K"], int(gsel["cur_n_e"])
+    for tol in (1e-8, 1e-4):
+        sel_e = CUR_device(torch.as_tensor(K[:n_e, :n_e], device="cuda"), tol)
+        sel_f = CUR_device(torch.as_tensor(K[n_e:, n_e:], device="cuda"), tol)
+        ref_e, ref_f, omega = gsel["cur_e_%g" % tol], gsel["cur_f_%g" % tol], gsel["cur_f_omega_%g" % tol]
+        assert len(sel_e) == len(ref_e) and len(sel_f) == len(ref_f)
+        # rows whose leverage is separated from the cut by more than rounding must agree exactly; ties (exact duplicates have
+        # equal leverage in both copies) may be resolved either way by the eigen-solver
+        cut = np.sort(omega)[::-1][len(ref_f) - 1] if len(ref_f) else 0.0
+        sure = set(np.flatnonzero(omega > cut + 1e-6))
+        assert sure <= set(int(i) for i in sel_f) and sure <= set(int(i) for i in ref_f)
+        assert np.all(omega[sel_f] >= cut - 1e-6)

@@ -1,6 +1,10 @@
 """CPU: host-side logic of the drop-in (layouts, block assembly, selection, sharding, bookkeeping)."""
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from helpers import make_force, make_energy
 
@@ -338,3 +342,16 @@ def test_inverse_rows_gradient_algebra_in_numpy():
                     for j in range(NE):
                         got += (alpha[i] * alpha[j] - Einv[j, i]) * dK[i, j]
     assert abs(got - want) <= 1e-10 * abs(want)
+
+
+def test_gpr_calc_import_alias():
+    """The reference's import paths (README.md:34-71) resolve to the B200 modules themselves."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from gpr_calc.gaussianprocess import GP\nfrom gpr_calc.calculator import GPR\n"
+            "from gpr_calc.kernels.RBF_mb import RBF_mb\nfrom gpr_calc.kernels.Dot_mb import Dot_mb\nfrom gpr_calc.SO3 import SO3\n"
+            "from gpr_calc.utilities import list_to_tuple\nimport gpr_calculator_b200.gaussianprocess as g, gpr_calculator_b200.SO3 as s\n"
+            "assert GP is g.GP and SO3 is s.SO3 and RBF_mb(para=[1.0, 0.1]).l == 0.1\nprint('alias ok')\n" % ROOT)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "alias ok" in res.stdout, res.stderr[-2000:]
