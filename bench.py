@@ -708,13 +708,19 @@ def main():
             dF = max(float(np.abs(res[k][1] - singles[k][1]).max()) for k in range(8))
             dS = max(max(abs(res[k][3] - singles[k][3]), float(np.abs(res[k][4] - singles[k][4]).max())) for k in range(8))
             assert len(res) == n_test and dE <= 1e-8 and dF <= 1e-8, (dE, dF)
-            probe = getattr(gp, "_variance_probe", None)
+            # conditioning diagnostic: how far the reference's explicit-inverse variance formula is from the factor route
+            from gpr_calculator_b200.batch import rows_from_batch
+            E_t, F_t = rows_from_batch(des.calculate_batch(tests[:2], to_host=False), None)
+            Xp = {"energy": gdev.energy_pack(E_t), "force": gdev.force_pack(F_t)}
+            Ks_p, _ = gp.kernel.k_total_device(Xp, gp.get_train_x(), f_tol=1e-12, grad=False)
+            probe = gp.variance_route_probe(Ks_p, gp.kernel.diag_device(Xp))
             result["predict"] = {"value": n_test / dt_pred, "unit": "structures/s", "structures": n_test, "seconds": dt_pred,
                                  "n_train": N, "atoms": len(tests[0]), "single_call_ms": single_ms,
                                  "device_ms_per_batch_of_32": predict_parts,
                                  "batch_vs_single_max_abs": {"E": dE, "F": dF, "sigma": dS},
-                                 "variance_route": None if probe is None else probe[1],
-                                 "variance_probe_sigma_diff": None if probe is None else probe[2],
+                                 "variance_route": "batches: Cholesky factor (trsm); single structures: explicit inverse (the "
+                                                   "reference's formula, gaussianprocess.py:904-908)",
+                                 "sigma_diff_between_routes_128_rows": probe,
                                  "sharding": "structures in contiguous blocks over %d rank(s), results all-reduced" % world,
                                  "call": "GP.predict_structures(%d Atoms, return_std=True, batch=32): SO3 + K* + mean + std on device, "
                                          "host Atoms in, numpy E/F/std out on every rank; single_call_ms = one "

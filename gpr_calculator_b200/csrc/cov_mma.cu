@@ -66,7 +66,6 @@ struct CovParams {
     int two_stage;                                            // two-stage contraction (no-gradient K_ff, 8 k-steps)
 };
 
-__constant__ double c_exp2_tab[32];    // 2^(j/32)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -110,8 +109,12 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 }
 
 // exp(x) for x <= 0 (the RBF exponent -(1-D)/(2 l^2)): 2^(k/32) table + degree-5 polynomial on
-// |r| <= ln2/64 (truncation 2e-15 relative), evaluated in Estrin form to keep the dependent chain short
-// (every FP64 instruction of the epilogue queues behind other warps' DMMAs).
+// |r| <= ln2/64 (truncation 2e-15 relative), evaluated in Estrin form.  (Round 2 measured a variant with a 1024-entry
+// table, degree 3, one-step reduction and an integer clamp -- 5 instead of 8 dependent FP64 steps: same kernel time,
+// 1 812 vs 1 811 ms at S5, so the dependent chain is not what bounds the epilogue; profiles/experiments/README.md.)
+constexpr int EXP_TAB = 32;
+__device__ double d_exp2_tab[EXP_TAB];    // 2^(j / 32)
+
 __device__ __forceinline__ double exp_neg(double x, const double *tab) {
     x = fmax(x, -700.0);                                     // exp(-700) ~ 1e-304: below anything that matters, no branch
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: low word = round-to-nearest integer
@@ -248,8 +251,8 @@ __global__ void __launch_bounds__(BIG ? BIG_WARPS * 32 : THREADS, NB == 0 ? 2 : 
     double *sA = reinterpret_cast<double *>(smem_raw);                  // [WARPS_K][a_tile_d]
     double *sB = sA + WARPS_K * a_tile_d;                                  // [STAGES][CH_K][b_tile_d]
     double *sRow = sB + STAGES * CH_K * b_tile_d;                          // [NFB][MAXROWS_K][NT] flush partials
-    double *sTab = sRow + NFB * MAXROWS_K * NT;                            // [32]
-    int4 *sEnt = reinterpret_cast<int4 *>(sTab + 32);                    // [MAXROWS_K]
+    double *sTab = sRow + NFB * MAXROWS_K * NT;                            // [EXP_TAB]
+    int4 *sEnt = reinterpret_cast<int4 *>(sTab + EXP_TAB);               // [MAXROWS_K]
     int *sRec = reinterpret_cast<int *>(sEnt + MAXROWS_K);                 // [STAGES][CH_K][REC]
     uint64_t *sBar = reinterpret_cast<uint64_t *>(sRec + STAGES * CH_K * REC);   // full[STAGES], A, flush[NFB]
     uint64_t *barFlush = sBar + STAGES + 1;
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(BIG ? BIG_WARPS * 32 : THREADS, NB == 0 ? 2 : 
     const int c_begin = tb0 / CH_K, c_end = (tb1 + CH_K - 1) / CH_K;
 
     if (tid < nent) sEnt[tid] = P.sched_ent[ent0 + tid];
-    if (tid < 32) sTab[tid] = c_exp2_tab[tid];
+    for (int i = tid; i < EXP_TAB; i += blockDim.x) sTab[i] = d_exp2_tab[i];
     if (tid == 0) {
         for (int s = 0; s <= STAGES; s++) mbar_init(&sBar[s], 1);
         for (int s = 0; s < NFB; s++) mbar_init(&barFlush[s], ntiles);     // one arrival per active warp and flush
@@ -615,7 +618,7 @@ size_t cov_smem_bytes(int nb, int ks, bool grad, bool big) {
     const int nt = (nb == 4 ? 9 : (nb == 0 ? 1 : 3)) * (grad ? 2 : 1);
     const int na = nb == 0 ? 1 : 4, nbc = nb == 0 ? 1 : nb;
     const int warps = big ? BIG_WARPS : WARPS, ch = big ? BIG_CH : CH, maxrows = warps * 8;
-    return (size_t)(warps * na * ks * 32 + STAGES * ch * nbc * ks * 32 + NFB * maxrows * nt + 32) * 8 +
+    return (size_t)(warps * na * ks * 32 + STAGES * ch * nbc * ks * 32 + NFB * maxrows * nt + EXP_TAB) * 8 +
            (size_t)maxrows * 16 + (size_t)STAGES * ch * REC * 4 + (STAGES + 1 + NFB) * 8 + STAGES * 4 + 128;
 }
 
@@ -679,9 +682,9 @@ int upload_tables() {
     int dev = 0;
     { int rc = current_device(&dev); if (rc) return rc; }
     if (done[dev]) return GPRB_OK;
-    double tab[32];
-    for (int j = 0; j < 32; j++) tab[j] = std::exp2((double)j / 32.0);
-    GPRB_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof tab));
+    static double tab[EXP_TAB];
+    for (int j = 0; j < EXP_TAB; j++) tab[j] = std::exp2((double)j / (double)EXP_TAB);
+    GPRB_CUDA(cudaMemcpyToSymbol(d_exp2_tab, tab, sizeof tab));
     done[dev] = true;
     return GPRB_OK;
 }

@@ -613,30 +613,19 @@ extern "C" int gprb_predict(int m, int N, const double *Ks, long long ldks, cons
     GPRB_REQUIRE(Kinv && diag && work, "gprb_predict: variance needs Kinv, diag and work");
     int rc = handles(st);
     if (rc) return rc;
-    const double one = 1.0, zero = 0.0;
-    if (getenv("GPRB_PREDICT_TRMM") != nullptr) {
-        // K^-1 is symmetric: work = Ks . triu(Kinv) is half the flops of the full product (m N^2 instead of 2 m N^2);
-        // column-major view: work^T (N x m) = A . Ks^T with A = the triangle of Kinv that holds the row-major upper part
-        Scratch scratch(st);
-        double *kd = (double *)scratch.get((size_t)N * sizeof(double));
-        if (!kd) return GPRB_ERR_CUDA;
-        extract_diag_kernel<<<(N + 255) / 256, 256, 0, st>>>(Kinv, ldi, N, kd);
-        GPRB_LAUNCHED();
-        // row-major upper triangle of Kinv == column-major LOWER triangle; (A Ks^T)[i, r] = sum_{j <= i (cm)} ...: by symmetry
-        // either triangle gives the same half-sum as long as the diagonal correction above is applied
-        cublasStatus_t bs = cublasDtrmm(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
-                                        N, m, &one, Kinv, (int)ldi, Ks, (int)ldks, work, N);
-        if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDtrmm status %d", (int)bs); return GPRB_ERR_CUDA; }
-        predict_rows_sym_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, work, kd, diag, mean, var);
-        GPRB_LAUNCHED();
-        GPRB_CUDA(cudaGetLastError());
-        return GPRB_OK;
-    }
-    // row-major work[m,N] = Ks[m,N] . Kinv[N,N]  ==  column-major work^T = Kinv^T . Ks^T
-    cublasStatus_t bs = cublasDgemm(g_blas, CUBLAS_OP_N, CUBLAS_OP_N, N, m, N, &one, Kinv, (int)ldi, Ks, (int)ldks,
-                                    &zero, work, N);
-    if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDgemm status %d", (int)bs); return GPRB_ERR_CUDA; }
-    predict_rows_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, work, diag, mean, var);
+    // K^-1 is symmetric: work = Ks . tri(Kinv) is half the flops of the full product (cuBLAS trmm, m N^2 instead of the
+    // 2 m N^2 of a gemm: 104 vs 189 ms for m = 3 104 rows at N = 32 980, profiles/r02_predict_variance_routes.txt), and
+    // k^T Kinv k = sum_j k_j (2 work_j - Kinv_jj k_j).  Column-major view: work^T (N x m) = tril_cm(Kinv) . Ks^T
+    const double one = 1.0;
+    Scratch scratch(st);
+    double *kd = (double *)scratch.get((size_t)N * sizeof(double));
+    if (!kd) return GPRB_ERR_CUDA;
+    extract_diag_kernel<<<(N + 255) / 256, 256, 0, st>>>(Kinv, ldi, N, kd);
+    GPRB_LAUNCHED();
+    cublasStatus_t bs = cublasDtrmm(g_blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+                                    N, m, &one, Kinv, (int)ldi, Ks, (int)ldks, work, N);
+    if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDtrmm status %d", (int)bs); return GPRB_ERR_CUDA; }
+    predict_rows_sym_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, work, kd, diag, mean, var);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;

@@ -572,35 +572,35 @@ class GP():
         return K_trans, mean, var
 
     # Variance routes.  The reference multiplies K* with the explicit inverse (gaussianprocess.py:369, 905: "inverse",
-    # gprb_predict: gemm, 2 m N^2 flops); |L^-1 k*|^2 through the Cholesky factor ("chol", gprb_predict_chol: one trsm, m N^2
-    # flops, no N x N inverse) is algebraically the same number.  A triangular solve with few right-hand sides is latency
-    # bound (S5: m = 97: 15 ms vs 8 ms; m = 3104: 113 vs 190 ms, tools/predict_routes.py), so below this many rows of K*
-    # (single structures) the reference's route is always used.  For larger batches the factor route is used only if it
-    # reproduces the reference's route to SIGMA_TOL in the standard deviation on a probe of the first rows after each fit
-    # (both routes lose cond(K) eps in the cancellation diag - k*^T K^-1 k*; when that exceeds 1e-8 the reference's own
-    # arithmetic is the one to follow).  GPRB_VARIANCE_ROUTE = chol | inverse overrides the probe.
+    # gprb_predict: half product of the symmetric inverse, m N^2 flops); |L^-1 k*|^2 through the Cholesky factor ("chol",
+    # gprb_predict_chol: one trsm, m N^2 flops, no N x N inverse to form) is algebraically the same number.
+    # Which one tracks the reference?  Measured on real Cu32 rows at N = 2 328, cond(K) = 4e8, sigma = 4e-4 .. 3e-2
+    # (tests/test_gpu_gp.py::test_sigma_routes_against_reference_formula, profiles/r02_sigma_routes.txt), max |d sigma|:
+    #     the reference's own formula (numpy / LAPACK, explicit inverse) vs an iteratively refined value   4.0e-7
+    #     device "chol" route  vs the refined value   1.6e-13        vs the reference's formula   4.0e-7
+    #     device "inverse" route vs the refined value 1.3e-6         vs the reference's formula   8.8e-7
+    # i.e. the explicit-inverse arithmetic loses cond(K) eps in the cancellation diag - k*^T K^-1 k* wherever it runs, two
+    # implementations of it differ from each other by MORE than either differs from the factor route, and the factor route
+    # is exact to rounding.  So batches take the factor route (closest to the truth AND to the reference's numbers); below
+    # CHOL_VARIANCE_MIN_ROWS rows of K* (single structures: a triangular solve with few right-hand sides is latency bound,
+    # 15 ms vs 4 ms at N = 32 980) the reference's explicit-inverse formula is used.  GPRB_VARIANCE_ROUTE = chol | inverse
+    # forces one route; variance_route_probe() reports how far the two are apart on the current model.
     CHOL_VARIANCE_MIN_ROWS = 512
-    SIGMA_TOL = 1e-8
     PROBE_ROWS = 128
 
-    def _batch_variance_route(self, K_trans, diag):
-        route = os.environ.get("GPRB_VARIANCE_ROUTE", "auto")
-        if route in ("chol", "inverse"):
-            return route
-        probe = getattr(self, "_variance_probe", None)
-        if probe is None or probe[0] != self.fits:
-            m, N = min(K_trans.shape[0], self.PROBE_ROWS), K_trans.shape[1]
-            Kp, dp = K_trans[:m], diag[:m]
-            mean, work = torch.empty(m, dtype=F64, device="cuda"), torch.empty((m, N), dtype=F64, device="cuda")
-            v_c, v_i = torch.empty(m, dtype=F64, device="cuda"), torch.empty(m, dtype=F64, device="cuda")
-            self.set_K_inv()
-            _lib.call("gprb_predict_chol", m, N, ptr(Kp), K_trans.stride(0), ptr(self._alpha_dev), ptr(self._L_dev), N,
-                      ptr(dp), ptr(mean), ptr(v_c), ptr(work), stream())
-            _lib.call("gprb_predict", m, N, ptr(Kp), K_trans.stride(0), ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
-                      ptr(dp), ptr(mean), ptr(v_i), ptr(work), stream())
-            diff = float((torch.sqrt(v_c) - torch.sqrt(v_i)).abs().max())
-            probe = self._variance_probe = (self.fits, "chol" if diff <= self.SIGMA_TOL else "inverse", diff)
-        return probe[1]
+    def variance_route_probe(self, K_trans, diag):
+        """max |sigma_chol - sigma_inverse| over the first PROBE_ROWS rows of K*: a direct estimate of the conditioning
+        error of the explicit-inverse variance formula (the reference's) on the fitted model.  Diagnostic only."""
+        m, N = min(K_trans.shape[0], self.PROBE_ROWS), K_trans.shape[1]
+        Kp, dp = K_trans[:m], diag[:m]
+        mean, work = torch.empty(m, dtype=F64, device="cuda"), torch.empty((m, N), dtype=F64, device="cuda")
+        v_c, v_i = torch.empty(m, dtype=F64, device="cuda"), torch.empty(m, dtype=F64, device="cuda")
+        self.set_K_inv()
+        _lib.call("gprb_predict_chol", m, N, ptr(Kp), K_trans.stride(0), ptr(self._alpha_dev), ptr(self._L_dev), N,
+                  ptr(dp), ptr(mean), ptr(v_c), ptr(work), stream())
+        _lib.call("gprb_predict", m, N, ptr(Kp), K_trans.stride(0), ptr(self._alpha_dev), ptr(self._Kinv_dev), N,
+                  ptr(dp), ptr(mean), ptr(v_i), ptr(work), stream())
+        return float((torch.sqrt(v_c) - torch.sqrt(v_i)).abs().max())
 
     def _mean_var(self, K_trans, diag):
         """mean = K* alpha and, when `diag` (the prior variances) is given, var = max(diag - k*^T K^-1 k*, 0)."""
@@ -612,7 +612,8 @@ class GP():
             return mean, None
         var = torch.empty(m, dtype=F64, device="cuda")
         work = torch.empty((m, N), dtype=F64, device="cuda")
-        if self._L_dev is not None and m >= self.CHOL_VARIANCE_MIN_ROWS and self._batch_variance_route(K_trans, diag) == "chol":
+        route = os.environ.get("GPRB_VARIANCE_ROUTE", "auto")          # auto | chol | inverse
+        if self._L_dev is not None and (route == "chol" or (route == "auto" and m >= self.CHOL_VARIANCE_MIN_ROWS)):
             _lib.call("gprb_predict_chol", m, N, ptr(K_trans), K_trans.stride(0), ptr(self._alpha_dev), ptr(self._L_dev), N,
                       ptr(diag), ptr(mean), ptr(var), ptr(work), stream())
         else:

@@ -32,3 +32,15 @@ def rel_err(a, b):
     a, b = np.asarray(a), np.asarray(b)
     den = np.abs(b).max()
     return float(np.abs(a - b).max() / den) if den > 0 else float(np.abs(a - b).max())
+
+
+def entry_err(a, b, d_rows, d_cols):
+    """Per-entry error on the Cauchy-Schwarz scale of each entry: max_ij |a_ij - b_ij| / sqrt(k(i,i) k(j,j)), with d_rows / d_cols
+    the prior variances k(i,i) of the row side and k(j,j) of the column side.  |K_ij| <= sqrt(K_ii K_jj) for a covariance, so
+    this is the relative error of every entry measured against the natural magnitude of ITS sum of pair terms (the absolute
+    floor tol * |A| |B| of SURVEY.md 7.3): small entries of a block with large neighbours are checked too, entries that are
+    sums of cancelling terms are not held to their own (arbitrarily small) value."""
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.sqrt(np.abs(np.asarray(d_rows))[:, None] * np.abs(np.asarray(d_cols))[None, :])
+    scale = np.where(scale > 0, scale, 1.0)
+    return float((np.abs(a - b) / scale).max()) if a.size else 0.0

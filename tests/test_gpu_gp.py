@@ -350,8 +350,8 @@ def test_sigma_routes_against_reference_formula(monkeypatch, capsys):
     """Pins sigma of both device variance routes in the benchmark's regime (real Cu32 rows, l = 0.1, noise 0.002 / 0.1,
     N = 24 + 2 304 = 2 328): against the reference's own formula evaluated in numpy / LAPACK on the same K, and against an
     iteratively refined value.  Tolerances are what each route meets here (printed; recorded in
-    profiles/r02_sigma_routes.txt); the batch route is chosen by GP._batch_variance_route from a probe of exactly this
-    difference, with the reference's route as the fall-back when 1e-8 is not met."""
+    profiles/r02_sigma_routes.txt).  Outcome: the factor route is exact to rounding and closer to the reference's numbers
+    than a second implementation of the reference's explicit-inverse formula is, so it is the batch route (GP._mean_var)."""
     import torch
     from gpr_calculator_b200 import synthetic as syn, device as gdev
     from gpr_calculator_b200.gaussianprocess import GP
@@ -377,15 +377,17 @@ def test_sigma_routes_against_reference_formula(monkeypatch, capsys):
     idx = np.arange(len(Kn))
     Kn[idx, idx] += np.where(idx < 24, 0.002 ** 2, 0.1 ** 2)
     Ks_h, prior_h = Ks.cpu().numpy(), prior.cpu().numpy()
+    sub = np.arange(0, Ks_h.shape[0], 8)             # the extended-precision refinement is slow: every 8th row of K*
     sig_ref, L = _sigma_reference_formula(Kn, Ks_h, prior_h)
-    sig_true = _sigma_refined(L, Kn, Ks_h, prior_h)
+    sig_ref = sig_ref[sub]
+    sig_true = _sigma_refined(L, Kn, Ks_h[sub], prior_h[sub])
     got = {}
     for route in ("inverse", "chol"):
         monkeypatch.setenv("GPRB_VARIANCE_ROUTE", route)
         _, var = gp._mean_var(Ks, prior)
-        got[route] = np.sqrt(var.cpu().numpy())
+        got[route] = np.sqrt(var.cpu().numpy())[sub]
     monkeypatch.delenv("GPRB_VARIANCE_ROUTE")
-    chosen = gp._batch_variance_route(Ks, prior)
+    probe = gp.variance_route_probe(Ks, prior)
     d = {"reference formula vs refined": np.abs(sig_ref - sig_true).max(),
          "device inverse route vs reference formula": np.abs(got["inverse"] - sig_ref).max(),
          "device chol route vs reference formula": np.abs(got["chol"] - sig_ref).max(),
@@ -393,15 +395,19 @@ def test_sigma_routes_against_reference_formula(monkeypatch, capsys):
          "device chol route vs refined": np.abs(got["chol"] - sig_true).max(),
          "device chol vs device inverse": np.abs(got["chol"] - got["inverse"]).max()}
     with capsys.disabled():
-        print("\n[sigma routes] N = %d, m = %d, cond(K) = %.3g, sigma range %.3g .. %.3g, probe picks '%s' (diff %.3g)"
-              % (len(Kn), len(sig_ref), np.linalg.cond(Kn), sig_true.min(), sig_true.max(), chosen, gp._variance_probe[2]))
+        print("\n[sigma routes] N = %d, m = %d, cond(K) = %.3g, sigma range %.3g .. %.3g, probe (first 128 rows) %.3g"
+              % (len(Kn), len(sig_ref), np.linalg.cond(Kn), sig_true.min(), sig_true.max(), probe))
         for k, v in d.items():
             print("[sigma routes]   max |d sigma|  %-44s %.3e" % (k, v))
-    # the reference's own formula is only this close to the refined value: no route can be asked for more
+    # pinned tolerances (what each route meets in this regime):
+    #   the factor route reproduces the refined value to rounding: 1e-8 in sigma with four orders of margin
+    assert d["device chol route vs refined"] <= 1e-10
+    #   the reference's own formula is only `floor` away from the refined value: no implementation of that formula can be
+    #   asked for more, and the factor route is as close to the reference's numbers as the reference is to the truth
     floor = max(1e-8, 4.0 * d["reference formula vs refined"])
     assert d["device inverse route vs reference formula"] <= floor
-    assert d["device chol route vs refined"] <= floor
-    assert chosen in ("chol", "inverse") and (chosen == "chol") == (gp._variance_probe[2] <= 1e-8)
+    assert d["device chol route vs reference formula"] <= 1.01 * d["reference formula vs refined"] + 1e-10
+    assert probe <= 2.0 * floor
 
 
 @pytest.fixture(scope="module")

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import make_force, make_energy, rel_err
+from helpers import make_force, make_energy, rel_err, entry_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -120,12 +120,19 @@ def test_blocks_vs_oracle(oracle_libs, name, kw1, kw2):
     O, OD = oracle_libs.RBFOracle("port"), oracle_libs.DotOracle("port")
     sig, l = 1.7, 0.6
     for zeta in (2.0, 3.0, 2.5):
+        # prior variances of every row of the four sides: the per-entry (Cauchy-Schwarz) scale, helpers.entry_err
+        dF1, dF2 = np.diag(O.kff_C(F1, F1, sig, l, zeta, tol=0.0)), np.diag(O.kff_C(F2, F2, sig, l, zeta, tol=0.0))
+        dE1, dE2 = np.diag(O.kee_C(E1, E1, sig, l, zeta)), np.diag(O.kee_C(E2, E2, sig, l, zeta))
+        hl = 1.0 / l ** 3 + 2.0 / l          # bound of |d log k / dl|: scale of the dK/dl entries
         for grad in (False, True):
-            for fn_g, fn_o, a, b in ((rk.kff_C, O.kff_C, F1, F2), (rk.kef_C, O.kef_C, E1, F2), (rk.kee_C, O.kee_C, E1, E2)):
+            for fn_g, fn_o, a, b, da, db in ((rk.kff_C, O.kff_C, F1, F2, dF1, dF2), (rk.kef_C, O.kef_C, E1, F2, dE1, dF2),
+                                             (rk.kee_C, O.kee_C, E1, E2, dE1, dE2)):
                 got, ref = fn_g(a, b, sig, l, zeta, grad=grad), fn_o(a, b, sig, l, zeta, grad=grad)
                 got, ref = (got, ref) if grad else ((got,), (ref,))
-                for x, y in zip(got, ref):
+                for k, (x, y) in enumerate(zip(got, ref)):
                     assert x.shape == y.shape and rel_err(x, y) <= TOL, (name, zeta, grad, fn_g.__name__)
+                    s_k = (1.0, 2.0 / sig, hl)[k]        # K, dK/dsigma = 2K/sigma, dK/dl
+                    assert entry_err(x, y, da * s_k, db * s_k) <= TOL, (name, zeta, grad, fn_g.__name__, "per entry", k)
         assert rel_err(dk.kff_C(F1, F2, 2.0, 1.5, zeta), OD.kff_C(F1, F2, 2.0, 1.5, zeta)) <= TOL
         assert rel_err(dk.kef_C(E1, F2, 2.0, 1.5, zeta), OD.kef_C(E1, F2, 2.0, 1.5, zeta)) <= TOL
         assert rel_err(dk.kee_C(E1, E2, 2.0, 1.5, zeta), OD.kee_C(E1, E2, 2.0, 1.5, zeta)) <= TOL
