@@ -34,7 +34,9 @@ def main():
     def make_gp():
         gp = GP(kernel=RBF_mb(para=[1.0, 0.1], zeta=2.0), descriptor=des, noise_e=0.002, noise_f=0.1, log_file=None)
         gp.train_x = {"energy": e_pack, "force": f_pack}
-        gp.y_train = y
+        gp.train_y = {"energy": list(y[:n_struct, 0]), "force": y[n_struct:, 0].reshape(-1, 3)}
+        gp.update_y_train()
+        gp.N_energy, gp.N_forces = e_pack.n_groups, f_pack.n_groups
         return gp
 
     # single-GPU build of the whole matrix on every rank (symmetric mode, no sharding)
@@ -98,7 +100,28 @@ def main():
         gd_.release_peer()
     dot_ok = (abs(dot["rows"][0] - dot["fullinv"][0]) <= 1e-9 * abs(dot["fullinv"][0])
               and np.allclose(dot["rows"][1], dot["fullinv"][1], rtol=1e-7, atol=1e-7))
-    ok = (results["peer"][1] <= 1e-12 and results["nccl"][1] <= 1e-12 and results["peer"][2] <= 1e-12 and same
+    # sharded prediction (structures split over the ranks, results all-reduced) against every rank predicting everything,
+    # and a full fit with the optimiser values broadcast from rank 0: identical hyper-parameters on every rank
+    os.environ["GPRB_NO_PEER"] = "0"
+    os.environ["GPRB_FULL_INVERSE"] = "0"
+    gpp = make_gp()
+    gpp.fit(opt=True, show=False, maxiter=3)
+    theta_fit = torch.tensor(gpp.kernel.parameters(), dtype=torch.float64, device="cuda")
+    lo, hi = theta_fit.clone(), theta_fit.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same_theta = bool(torch.equal(lo, hi))
+    tests_ = [a for a, _, _ in syn.structures(2 * world + 3, 2, 3000)]
+    sharded = gpp.predict_structures(tests_, return_std=True, f_tol=1e-12, batch=4)
+    local = gpp.predict_structures(tests_, return_std=True, f_tol=1e-12, batch=4, shard=False)
+    pred_err = max(max(abs(a[0] - b[0]), float(np.abs(a[1] - b[1]).max()), abs(a[3] - b[3]), float(np.abs(a[4] - b[4]).max()))
+                   for a, b in zip(sharded, local))
+    gpp.release_peer()
+    pred_ok = len(sharded) == len(tests_) and pred_err <= 1e-9 and same_theta
+    if rank == 0:
+        print("sharded prediction max |diff| vs replicated %.2e, fitted theta identical on all ranks: %s (%s)"
+              % (pred_err, same_theta, gpp.kernel.parameters()), flush=True)
+    ok = (pred_ok and results["peer"][1] <= 1e-12 and results["nccl"][1] <= 1e-12 and results["peer"][2] <= 1e-12 and same
           and abs(lml_p - lml_n) <= 1e-9 * abs(lml_n) and np.allclose(g_p, g_n, rtol=1e-9, atol=1e-9)
           and abs(lml_p - lml_f) <= 1e-9 * abs(lml_f) and np.allclose(g_p, g_f, rtol=1e-7, atol=1e-7) and dot_ok)
     if rank == 0:
