@@ -175,26 +175,34 @@ __global__ void so3_radial_kernel(int n_nb, const double *__restrict__ nb_rvec, 
 
 // Normalised Y_lm for 0 <= m <= l <= L into Y[(l*(L+1)+m)] (complex), Condon-Shortley phase,
 // the convention of scipy.special.sph_harm_y used by the reference (SO3.py:679).
-// One thread per m; ct = cos(theta), st = sin(theta), (cp, sp) = (cos phi, sin phi).
-__device__ void ylm_column(int m, int L, double ct, double st, double cp, double sp, cuDoubleComplex *Y) {
-    // Ybar_m^m
-    double pmm = sqrt(1.0 / (4.0 * PI));
-    for (int k = 1; k <= m; k++) pmm *= -sqrt((2.0 * k + 1.0) / (2.0 * k)) * st;
-    // e^{i m phi}
-    double cm = 1.0, sm_ = 0.0;
+// One lane per m; ct = cos(theta), st = sin(theta), (cp, sp) = (cos phi, sin phi).  The square-root factors of the
+// recurrences come from tables built once per CTA (ylm_tables): tp[k] = -sqrt((2k+1)/(2k)), ta / tb [l*(L+1)+m].
+__device__ void ylm_column(int m, int L, double ct, double st, double cp, double sp, const double *tp, const double *ta,
+                           const double *tb, cuDoubleComplex *Y) {
+    double pmm = 0.28209479177387814347;      // sqrt(1 / 4 pi)
+    for (int k = 1; k <= m; k++) pmm *= tp[k] * st;
+    double cm = 1.0, sm_ = 0.0;                 // e^{i m phi}
     for (int k = 0; k < m; k++) { const double t = cm * cp - sm_ * sp; sm_ = sm_ * cp + cm * sp; cm = t; }
     double pl2 = 0.0, pl1 = pmm;
     Y[m * (L + 1) + m] = make_cuDoubleComplex(pmm * cm, pmm * sm_);
     for (int l = m + 1; l <= L; l++) {
-        double pl;
-        if (l == m + 1) pl = sqrt(2.0 * m + 3.0) * ct * pl1;
-        else {
-            const double a = sqrt((4.0 * l * l - 1.0) / ((double)l * l - (double)m * m));
-            const double b = sqrt((((double)l - 1.0) * (l - 1.0) - (double)m * m) / (4.0 * (l - 1.0) * (l - 1.0) - 1.0));
-            pl = a * (ct * pl1 - b * pl2);
-        }
+        const double pl = (l == m + 1) ? ta[l * (L + 1) + m] * ct * pl1 : ta[l * (L + 1) + m] * (ct * pl1 - tb[l * (L + 1) + m] * pl2);
         Y[l * (L + 1) + m] = make_cuDoubleComplex(pl * cm, pl * sm_);
         pl2 = pl1; pl1 = pl;
+    }
+}
+
+__device__ void ylm_tables(int L, int tid, int nt, double *tp, double *ta, double *tb) {
+    for (int k = tid; k <= L; k += nt) tp[k] = k ? -sqrt((2.0 * k + 1.0) / (2.0 * k)) : 0.0;
+    for (int e = tid; e < (L + 1) * (L + 1); e += nt) {
+        const int l = e / (L + 1), m = e % (L + 1);
+        double av = 0.0, bv = 0.0;
+        if (l == m + 1) av = sqrt(2.0 * m + 3.0);
+        else if (l > m + 1) {
+            av = sqrt((4.0 * l * l - 1.0) / ((double)l * l - (double)m * m));
+            bv = sqrt((((double)l - 1.0) * (l - 1.0) - (double)m * m) / (4.0 * (l - 1.0) * (l - 1.0) - 1.0));
+        }
+        ta[e] = av; tb[e] = bv;
     }
 }
 
@@ -214,71 +222,120 @@ struct SO3Power {
     const double *pos; const double *inv_vol; double *rdxdr;   // stress: rdxdr[n_seq][d][3][3] = -pstress / volume
 };
 
-// one CTA per centre atom
-__global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p) {
+// Shared-memory plan of so3_power_kernel (doubles unless noted), W = warps per CTA:
+//   CTA:      sC [nent] complex | coefficient tables: gradient of Y_lm [L1*M*6], Y recurrences tp [LY+1], ta, tb [(LY+1)^2]
+//   per warp: sdc [3 nent] complex (phase A: the warp's partial C_nlm) | sY [(LY+1)^2] complex | sAcc, sSelf [3 d] |
+//             stress: sAccR, sSelfR [9 d], sTot [3 d]
+__host__ __device__ inline size_t so3_power_cta_doubles(int nent, int L1, int M, int LY) {
+    const size_t n = (size_t)2 * nent + (size_t)6 * L1 * M + (size_t)(LY + 1) + (size_t)2 * (LY + 1) * (LY + 1);
+    return (n + 1) & ~(size_t)1;          // the per-warp regions start with complex numbers: keep them 16-byte aligned
+}
+__host__ __device__ inline size_t so3_power_warp_doubles(int nent, int d, int LY, bool stress) {
+    const size_t n = (size_t)6 * nent + (size_t)2 * (LY + 1) * (LY + 1) + (size_t)6 * d + (stress ? (size_t)21 * d : 0);
+    return (n + 1) & ~(size_t)1;
+}
+
+// One CTA per centre atom, W warps; every WARP owns whole neighbours (phase A) / whole groups of images of one neighbour
+// atom j (phase B) and works through them without CTA-wide barriers: the geometry scalars are computed redundantly by all
+// lanes, Y_lm by lanes 0..LY into the warp's own table, grad c_nlm by the lanes into the warp's own buffer, and every lane
+// owns fixed outputs of dP.  The square roots of the Y_lm / grad Y_lm recurrences are tabulated once per CTA.  CTA-wide
+// barriers: three (tables + zeroing, C_nlm complete, self rows complete).  (Round 1: one neighbour at a time for the
+// whole CTA with three barriers each and six square roots per c_nlm entry: 48 % of the stall samples were barriers.)
+__global__ void __launch_bounds__(128, 4) so3_power_kernel(SO3Power a, SO3Params p) {
     extern __shared__ __align__(16) unsigned char raw[];
     const int L1 = p.lmax + 1, M = 2 * p.lmax + 1, LY = p.lmax + 1;   // Y table up to l = lmax+1
     const int nent = p.nmax * L1 * M;
     const int npair = p.nmax * (p.nmax + 1) / 2, d = npair * L1;
-    cuDoubleComplex *sC = reinterpret_cast<cuDoubleComplex *>(raw);                 // [nent] C_tot
-    cuDoubleComplex *sdc = sC + nent;                                               // [nent][3] grad c(w)
-    cuDoubleComplex *sY = sdc + 3 * nent;                                           // [(LY+1)*(LY+1)]
-    double *sAcc = reinterpret_cast<double *>(sY + (LY + 1) * (LY + 1));            // [d*3] current j group
-    double *sSelf = sAcc + 3 * d;                                                   // [d*3] sum over j != i
-    double *sGeo = sSelf + 3 * d;                                                   // [16] per-neighbour scalars
-    double *sAccR = sGeo + 16;                                                      // [d*9] R_j (x) dP of the current j group
-    double *sSelfR = sAccR + 9 * d;                                                 // [d*9] the j == i group (own images)
-    double *sTot = sSelfR + 9 * d;                                                  // [d*3] sum of dP over all neighbours
     const bool stress = a.rdxdr != nullptr;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, W = nt >> 5;
+    double *base = reinterpret_cast<double *>(raw);
+    cuDoubleComplex *sC = reinterpret_cast<cuDoubleComplex *>(base);               // [nent] C_tot
+    double *sCoef = base + 2 * nent;                                               // [L1*M][6]
+    double *sTp = sCoef + 6 * L1 * M;                                              // [LY+1]
+    double *sTa = sTp + (LY + 1), *sTb = sTa + (LY + 1) * (LY + 1);
+    double *wbase = base + so3_power_cta_doubles(nent, L1, M, LY) + (size_t)warp * so3_power_warp_doubles(nent, d, LY, stress);
+    cuDoubleComplex *sdc = reinterpret_cast<cuDoubleComplex *>(wbase);             // [nent][3] grad c(w) of the warp's neighbour
+    cuDoubleComplex *sY = sdc + 3 * nent;                                          // [(LY+1)^2]
+    double *sAcc = reinterpret_cast<double *>(sY + (LY + 1) * (LY + 1));           // [d*3] current j group
+    double *sSelf = sAcc + 3 * d;                                                  // [d*3] the warp's sum over its groups j != i
+    double *sAccR = sSelf + 3 * d;                                                 // [d*9] R_j (x) dP of the current j group
+    double *sSelfR = sAccR + 9 * d;                                                // [d*9] the j == i group (own images)
+    double *sTot = sSelfR + 9 * d;                                                 // [d*3] the warp's sum of dP over its neighbours
+    const size_t wstride = so3_power_warp_doubles(nent, d, LY, stress);
     const int i = blockIdx.x;
     const int w0 = a.nb_ptr[i], w1 = a.nb_ptr[i + 1];
     const int a0 = a.atom_ptr[a.struct_of[i]];
     const int nnl = p.nmax * L1;
 
-    for (int e = tid; e < nent; e += nt) sC[e] = make_cuDoubleComplex(0.0, 0.0);
-    for (int o = tid; o < 3 * d; o += nt) { sAcc[o] = 0.0; sSelf[o] = 0.0; }
+    // ---- per-CTA tables -----------------------------------------------------------------------
+    ylm_tables(LY, tid, nt, sTp, sTa, sTb);
+    for (int e = tid; e < L1 * M; e += nt) {
+        // covariant spherical components of grad Y_lm (SO3.py:686-702): coefficients of Y_{l+1} and Y_{l-1}, without 1/r
+        const int l = e / M, m = e % M - p.lmax;
+        double *c = sCoef + 6 * e;
+        for (int k = 0; k < 6; k++) c[k] = 0.0;
+        if (l >= 1 && m >= -l && m <= l) {
+            const double dl = (double)l, dm = (double)m;
+            c[0] = -sqrt(((dl + 1) * (dl + 1) - dm * dm) / (2 * dl + 1) / (2 * dl + 3)) * dl;
+            if (abs(m) <= l - 1) c[1] = sqrt((dl * dl - dm * dm) / (2 * dl - 1) / (2 * dl + 1)) * (dl + 1);
+            c[2] = -sqrt((dl + dm + 1) * (dl + dm + 2) / 2 / (2 * dl + 1) / (2 * dl + 3)) * dl;
+            if (abs(m + 1) <= l - 1) c[3] = sqrt((dl - dm - 1) * (dl - dm) / 2 / (2 * dl - 1) / (2 * dl + 1)) * (dl + 1);
+            c[4] = -sqrt((dl - dm + 1) * (dl - dm + 2) / 2 / (2 * dl + 1) / (2 * dl + 3)) * dl;
+            if (abs(m - 1) <= l - 1) c[5] = sqrt((dl + dm - 1) * (dl + dm) / 2 / (2 * dl - 1) / (2 * dl + 1)) * (dl + 1);
+        }
+    }
+    for (int e = lane; e < 3 * nent; e += 32) sdc[e] = make_cuDoubleComplex(0.0, 0.0);      // phase A: partial C in sdc[0..nent)
+    for (int o = lane; o < 3 * d; o += 32) { sAcc[o] = 0.0; sSelf[o] = 0.0; }
     if (stress) {
-        for (int o = tid; o < 9 * d; o += nt) { sAccR[o] = 0.0; sSelfR[o] = 0.0; }
-        for (int o = tid; o < 3 * d; o += nt) sTot[o] = 0.0;
+        for (int o = lane; o < 9 * d; o += 32) { sAccR[o] = 0.0; sSelfR[o] = 0.0; }
+        for (int o = lane; o < 3 * d; o += 32) sTot[o] = 0.0;
     }
     __syncthreads();
 
+    // geometry of neighbour w: every lane computes the scalars, lanes 0..LY the columns of Y_lm (warp-local)
+    double g_r, g_ux, g_uy, g_uz, g_gauss, g_dgauss, g_fc, g_dfc, g_Z;
     auto geometry = [&](int w) {
-        // thread 0: scalars of neighbour w; threads 0..LY: Y_lm columns
         const double rx = a.nb_rvec[3 * w], ry = a.nb_rvec[3 * w + 1], rz = a.nb_rvec[3 * w + 2];
         const double r = sqrt(rx * rx + ry * ry + rz * rz);
         const double rxy = sqrt(rx * rx + ry * ry);
         const double ct = rz / r, st = rxy / r;
         const double cp = rxy > 0.0 ? rx / rxy : 1.0, sp = rxy > 0.0 ? ry / rxy : 0.0;
-        if (tid <= LY) ylm_column(tid, LY, ct, st, cp, sp, sY);
-        if (tid == 0) {
-            const double gauss = 4.0 * PI * exp(-p.alpha * r * r);
-            const double fc = 0.5 * (cos(PI * r / p.rcut) + 1.0);
-            const double dfc = -0.5 * PI / p.rcut * sin(PI * r / p.rcut);
-            sGeo[0] = r; sGeo[1] = rx / r; sGeo[2] = ry / r; sGeo[3] = rz / r;
-            sGeo[4] = gauss; sGeo[5] = -2.0 * p.alpha * r * gauss; sGeo[6] = fc; sGeo[7] = dfc;
-            // neighbour weight Z_j; weight_on: a neighbour of another species counts negative (SO3.py:381-385)
-            const int zj = a.numbers[a.nb_j[w]];
-            sGeo[8] = ((a.derivative & 2) && zj != a.numbers[i]) ? -(double)zj : (double)zj;
-        }
+        __syncwarp();                       // the previous neighbour's readers of sY are done
+        if (lane <= LY) ylm_column(lane, LY, ct, st, cp, sp, sTp, sTa, sTb, sY);
+        g_r = r; g_ux = rx / r; g_uy = ry / r; g_uz = rz / r;
+        g_gauss = 4.0 * PI * exp(-p.alpha * r * r);
+        g_dgauss = -2.0 * p.alpha * r * g_gauss;
+        g_fc = 0.5 * (cos(PI * r / p.rcut) + 1.0);
+        g_dfc = -0.5 * PI / p.rcut * sin(PI * r / p.rcut);
+        // neighbour weight Z_j; weight_on: a neighbour of another species counts negative (SO3.py:381-385)
+        const int zj = a.numbers[a.nb_j[w]];
+        g_Z = ((a.derivative & 2) && zj != a.numbers[i]) ? -(double)zj : (double)zj;
+        __syncwarp();
     };
 
-    // ---- phase A: C_tot = sum_w Z_j N_l 4pi e^{-a r^2} f_c Y_lm I_nl -----------------------------
-    for (int w = w0; w < w1; w++) {
+    // ---- phase A: C_tot = sum_w Z_j N_l 4pi e^{-a r^2} f_c Y_lm I_nl  (warp w % W, partial sums per warp) ----------
+    for (int w = w0 + warp; w < w1; w += W) {
         geometry(w);
-        __syncthreads();
-        const double pref = sGeo[8] * sGeo[4] * sGeo[6];
+        const double pref = g_Z * g_gauss * g_fc;
         const double *I = a.rad + (size_t)w * 2 * nnl;
-        for (int e = tid; e < nent; e += nt) {
+        for (int e = lane; e < nent; e += 32) {
             const int n = e / (L1 * M), l = (e / M) % L1, m = e % M - p.lmax;
             if (m < -l || m > l) continue;
             const cuDoubleComplex y = ylm_get(sY, LY, l, m);
             const double f = pref * p.norm_l[l] * I[n * L1 + l];
-            sC[e].x += f * y.x; sC[e].y += f * y.y;
+            sdc[e].x += f * y.x; sdc[e].y += f * y.y;
         }
-        __syncthreads();
     }
+    __syncthreads();
+    for (int e = tid; e < nent; e += nt) {           // fixed order over the warps: deterministic
+        double cx = 0.0, cy = 0.0;
+        for (int k = 0; k < W; k++) {
+            const cuDoubleComplex v = reinterpret_cast<const cuDoubleComplex *>(base + so3_power_cta_doubles(nent, L1, M, LY) + k * wstride)[e];
+            cx += v.x; cy += v.y;
+        }
+        sC[e] = make_cuDoubleComplex(cx, cy);
+    }
+    __syncthreads();
     // x_i = Re sum_m C_nlm conj(C_n'lm), tril(n >= n') x l   (SO3.py:248, 266)
     for (int o = tid; o < d; o += nt) {
         const int pr = o / L1, l = o % L1;
@@ -293,67 +350,51 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
     }
     if (!(a.derivative & 1)) return;
 
-    // ---- phase B: dP per neighbour, grouped by neighbour atom j -----------------------------------
-    int row = a.seq_ptr[i];
-    bool self_done = false;
-    int self_row = -1;
+    // ---- phase B: dP per neighbour, grouped by neighbour atom j; group g belongs to warp g % W -------------------
+    // rows of `seq` for centre i: the unique neighbour atoms in increasing order, the (i, i) row at its sorted position
+    int n_less = 0;
+    bool has_self = false;
+    {
+        int prev = -1;
+        for (int w = w0; w < w1; w++) {
+            const int j = a.nb_j[w];
+            if (j != prev) { prev = j; if (j < i) n_less++; if (j == i) has_self = true; }
+        }
+    }
+    const int row0 = a.seq_ptr[i];
+    const int self_row = row0 + n_less;
     const double isq2 = 0.70710678118654752440;
+    const double iv = stress ? a.inv_vol[a.struct_of[i]] : 0.0;
+    int g = -1, prev_j = -1;
     for (int w = w0; w < w1; w++) {
-        __syncthreads();          // previous iteration's readers of sdc / sY / sGeo are done
+        const int j = a.nb_j[w];
+        if (j != prev_j) { g++; prev_j = j; }
+        if (g % W != warp) continue;
         geometry(w);
-        __syncthreads();
-        const double r = sGeo[0], ux = sGeo[1], uy = sGeo[2], uz = sGeo[3];
-        const double gauss = sGeo[4], dgauss = sGeo[5], fc = sGeo[6], dfc = sGeo[7], Z = sGeo[8];
+        const double r = g_r, ir = 1.0 / g_r, gauss = g_gauss, dgauss = g_dgauss, fc = g_fc, dfc = g_dfc, Z = g_Z;
+        const double u[3] = {g_ux, g_uy, g_uz};
         const double *I = a.rad + (size_t)w * 2 * nnl;
         const double *dI = I + nnl;
-        for (int e = tid; e < nent; e += nt) {
+        (void)r;
+        for (int e = lane; e < nent; e += 32) {
             const int n = e / (L1 * M), l = (e / M) % L1, m = e % M - p.lmax;
             cuDoubleComplex g0 = make_cuDoubleComplex(0, 0), g1 = g0, g2 = g0;
             if (m >= -l && m <= l) {
                 const cuDoubleComplex y = ylm_get(sY, LY, l, m);
-                // covariant spherical components of grad Y_lm (SO3.py:686-702)
                 cuDoubleComplex c0 = make_cuDoubleComplex(0, 0), cpl = c0, cmi = c0;
                 if (l >= 1) {
-                    const double ir = 1.0 / r;
-                    const double dl = (double)l, dm = (double)m;
-                    {
-                        const double k1 = -sqrt(((dl + 1) * (dl + 1) - dm * dm) / (2 * dl + 1) / (2 * dl + 3)) * dl * ir;
-                        const cuDoubleComplex yu = ylm_get(sY, LY, l + 1, m);
-                        c0 = make_cuDoubleComplex(k1 * yu.x, k1 * yu.y);
-                        if (abs(m) <= l - 1) {
-                            const double k2 = sqrt((dl * dl - dm * dm) / (2 * dl - 1) / (2 * dl + 1)) * (dl + 1) * ir;
-                            const cuDoubleComplex yd = ylm_get(sY, LY, l - 1, m);
-                            c0.x += k2 * yd.x; c0.y += k2 * yd.y;
-                        }
-                    }
-                    {
-                        const double k1 = -sqrt((dl + dm + 1) * (dl + dm + 2) / 2 / (2 * dl + 1) / (2 * dl + 3)) * dl * ir;
-                        const cuDoubleComplex yu = ylm_get(sY, LY, l + 1, m + 1);
-                        cpl = make_cuDoubleComplex(k1 * yu.x, k1 * yu.y);
-                        if (abs(m + 1) <= l - 1) {
-                            const double k2 = sqrt((dl - dm - 1) * (dl - dm) / 2 / (2 * dl - 1) / (2 * dl + 1)) * (dl + 1) * ir;
-                            const cuDoubleComplex yd = ylm_get(sY, LY, l - 1, m + 1);
-                            cpl.x -= k2 * yd.x; cpl.y -= k2 * yd.y;
-                        }
-                    }
-                    {
-                        const double k1 = -sqrt((dl - dm + 1) * (dl - dm + 2) / 2 / (2 * dl + 1) / (2 * dl + 3)) * dl * ir;
-                        const cuDoubleComplex yu = ylm_get(sY, LY, l + 1, m - 1);
-                        cmi = make_cuDoubleComplex(k1 * yu.x, k1 * yu.y);
-                        if (abs(m - 1) <= l - 1) {
-                            const double k2 = sqrt((dl + dm - 1) * (dl + dm) / 2 / (2 * dl - 1) / (2 * dl + 1)) * (dl + 1) * ir;
-                            const cuDoubleComplex yd = ylm_get(sY, LY, l - 1, m - 1);
-                            cmi.x -= k2 * yd.x; cmi.y -= k2 * yd.y;
-                        }
-                    }
+                    const double *cf = sCoef + 6 * (l * M + m + p.lmax);
+                    const cuDoubleComplex yu0 = ylm_get(sY, LY, l + 1, m), yd0 = ylm_get(sY, LY, l - 1, m);
+                    const cuDoubleComplex yup = ylm_get(sY, LY, l + 1, m + 1), ydp = ylm_get(sY, LY, l - 1, m + 1);
+                    const cuDoubleComplex yum = ylm_get(sY, LY, l + 1, m - 1), ydm = ylm_get(sY, LY, l - 1, m - 1);
+                    c0 = make_cuDoubleComplex((cf[0] * yu0.x + cf[1] * yd0.x) * ir, (cf[0] * yu0.y + cf[1] * yd0.y) * ir);
+                    cpl = make_cuDoubleComplex((cf[2] * yup.x - cf[3] * ydp.x) * ir, (cf[2] * yup.y - cf[3] * ydp.y) * ir);
+                    cmi = make_cuDoubleComplex((cf[4] * yum.x - cf[5] * ydm.x) * ir, (cf[4] * yum.y - cf[5] * ydm.y) * ir);
                 }
                 // Cartesian gradient of Y (SO3.py:705-707): x = (c- - c+)/sqrt2, y = i (c- + c+)/sqrt2, z = c0
-                const cuDoubleComplex gyx = make_cuDoubleComplex((cmi.x - cpl.x) * isq2, (cmi.y - cpl.y) * isq2);
-                const cuDoubleComplex gyy = make_cuDoubleComplex(-(cmi.y + cpl.y) * isq2, (cmi.x + cpl.x) * isq2);
-                const cuDoubleComplex gyz = c0;
+                const cuDoubleComplex gy[3] = {make_cuDoubleComplex((cmi.x - cpl.x) * isq2, (cmi.y - cpl.y) * isq2),
+                                               make_cuDoubleComplex(-(cmi.y + cpl.y) * isq2, (cmi.x + cpl.x) * isq2), c0};
                 const double Inl = I[n * L1 + l], dInl = dI[n * L1 + l];
-                const double u[3] = {ux, uy, uz};
-                const cuDoubleComplex gy[3] = {gyx, gyy, gyz};
                 const double wl = Z * p.norm_l[l];
                 cuDoubleComplex out[3];
 #pragma unroll
@@ -367,9 +408,9 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
             }
             sdc[3 * e] = g0; sdc[3 * e + 1] = g1; sdc[3 * e + 2] = g2;
         }
-        __syncthreads();
+        __syncwarp();
         // dP[pair(n,n'), l, k] = Re sum_m [ dc_nlm conj(C_n'lm) + conj(dc_n'lm conj(C_nlm)) ]  (SO3.py:249-251)
-        for (int o = tid; o < 3 * d; o += nt) {
+        for (int o = lane; o < 3 * d; o += 32) {
             const int k = o % 3, pl = o / 3, pr = pl / L1, l = pl % L1;
             int n = 0; while ((n + 1) * (n + 2) / 2 <= pr) n++;
             const int n2 = pr - n * (n + 1) / 2;
@@ -381,47 +422,49 @@ __global__ void __launch_bounds__(128) so3_power_kernel(SO3Power a, SO3Params p)
                 s += d1.x * c2.x + d1.y * c2.y + d2.x * c1.x + d2.y * c1.y;
             }
             sAcc[o] += s;
-            if (stress) {      // pstress[(i,j)] -= R_j (x) dP(w), R_j = r_i + r_ij (SO3.py:226, 254, 264)
+            if (stress) {      // pstress[(i,j)] -= R_j (x) dP(w), R_j = r_i + r_ij (SO3.py:226, 254, 264); the lane owns (pl, :, k)
                 sTot[o] += s;
 #pragma unroll
                 for (int n3 = 0; n3 < 3; n3++)
                     sAccR[(pl * 3 + n3) * 3 + k] += (a.pos[3 * (size_t)i + n3] + a.nb_rvec[3 * (size_t)w + n3]) * s;
             }
         }
+        __syncwarp();
         // flush when the next neighbour belongs to another atom
-        if (stress) __syncthreads();      // the 9-column accumulators are re-partitioned over the threads below
-        const int j = a.nb_j[w];
         const bool last_of_j = (w + 1 == w1) || (a.nb_j[w + 1] != j);
-        if (last_of_j) {
-            if (!self_done && i < j) { self_row = row++; self_done = true; }
-            if (j == i) {
-                self_row = row++; self_done = true;
-                for (int o = tid; o < 3 * d; o += nt) sAcc[o] = 0.0;     // own images cancel (SO3.py:267-273)
-                if (stress) for (int o = tid; o < 9 * d; o += nt) { sSelfR[o] = sAccR[o]; sAccR[o] = 0.0; }
-            } else {
-                const int rj = row++;
-                for (int o = tid; o < 3 * d; o += nt) {
-                    const double v = sAcc[o];
-                    a.dxdr[(size_t)rj * 3 * d + o] = v;
-                    sSelf[o] += v;
-                    sAcc[o] = 0.0;
-                }
-                if (stress) {
-                    const double iv = a.inv_vol[a.struct_of[i]];
-                    for (int o = tid; o < 9 * d; o += nt) { a.rdxdr[(size_t)rj * 9 * d + o] = sAccR[o] * iv; sAccR[o] = 0.0; }
-                }
-                if (tid == 0) { a.seq[2 * (size_t)rj] = i - a0; a.seq[2 * (size_t)rj + 1] = j - a0; }
+        if (!last_of_j) continue;
+        if (j == i) {
+            for (int o = lane; o < 3 * d; o += 32) sAcc[o] = 0.0;        // own images cancel (SO3.py:267-273)
+            if (stress) for (int o = lane; o < 9 * d; o += 32) { sSelfR[o] = sAccR[o]; sAccR[o] = 0.0; }
+        } else {
+            const int rj = row0 + g + ((!has_self && j > i) ? 1 : 0);
+            for (int o = lane; o < 3 * d; o += 32) {
+                const double v = sAcc[o];
+                a.dxdr[(size_t)rj * 3 * d + o] = v;
+                sSelf[o] += v;
+                sAcc[o] = 0.0;
             }
+            if (stress) for (int o = lane; o < 9 * d; o += 32) { a.rdxdr[(size_t)rj * 9 * d + o] = sAccR[o] * iv; sAccR[o] = 0.0; }
+            if (lane == 0) { a.seq[2 * (size_t)rj] = i - a0; a.seq[2 * (size_t)rj + 1] = j - a0; }
         }
+        __syncwarp();
     }
-    if (!self_done) self_row = row++;
-    for (int o = tid; o < 3 * d; o += nt) a.dxdr[(size_t)self_row * 3 * d + o] = -sSelf[o];
+    __syncthreads();
+    // the (i, i) row: minus the sum over all j != i, combined over the warps in a fixed order
+    double *w0base = base + so3_power_cta_doubles(nent, L1, M, LY);
+    const size_t offSelf = (size_t)6 * nent + (size_t)2 * (LY + 1) * (LY + 1) + (size_t)3 * d;
+    for (int o = tid; o < 3 * d; o += nt) {
+        double s = 0.0;
+        for (int k = 0; k < W; k++) s += (w0base + k * wstride + offSelf)[o];
+        a.dxdr[(size_t)self_row * 3 * d + o] = -s;
+    }
     if (stress) {      // pstress[(i,i)] = -sum_{own images} R_j (x) dP + R_i (x) sum_w dP ; rdxdr = -pstress / vol
-        __syncthreads();
-        const double iv = a.inv_vol[a.struct_of[i]];
+        const size_t offSelfR = offSelf + (size_t)3 * d + (size_t)9 * d, offTot = offSelfR + (size_t)9 * d;
         for (int o = tid; o < 9 * d; o += nt) {
             const int k = o % 3, n3 = (o / 3) % 3, pl = o / 9;
-            a.rdxdr[(size_t)self_row * 9 * d + o] = (sSelfR[o] - a.pos[3 * (size_t)i + n3] * sTot[pl * 3 + k]) * iv;
+            double sr = 0.0, stot = 0.0;
+            for (int q = 0; q < W; q++) { sr += (w0base + q * wstride + offSelfR)[o]; stot += (w0base + q * wstride + offTot)[pl * 3 + k]; }
+            a.rdxdr[(size_t)self_row * 9 * d + o] = (sr - a.pos[3 * (size_t)i + n3] * stot) * iv;
         }
     }
     if (tid == 0) { a.seq[2 * (size_t)self_row] = i - a0; a.seq[2 * (size_t)self_row + 1] = i - a0; }
@@ -474,14 +517,20 @@ extern "C" int gprb_so3_power(int n_atoms, const int *nb_ptr, const int *nb_j, c
     SO3Power a{nb_ptr, nb_j, nb_rvec, rad, numbers, atom_ptr, struct_of, seq_ptr, x, dxdr, seq, derivative, pos, inv_vol, rdxdr};
     const int L1 = lmax + 1, M = 2 * lmax + 1, LY = lmax + 1;
     const int nent = nmax * L1 * M, d = nmax * (nmax + 1) / 2 * L1;
-    const size_t smem = (size_t)(4 * nent + (LY + 1) * (LY + 1)) * sizeof(cuDoubleComplex) + (size_t)(6 * d + 16 + 21 * d) * sizeof(double);
+    const size_t cta_b = so3_power_cta_doubles(nent, L1, M, LY) * sizeof(double);
+    const size_t warp_b = so3_power_warp_doubles(nent, d, LY, rdxdr != nullptr) * sizeof(double);
+    int warps = 4;                                   // warps per centre atom (four CTAs per SM); fewer if one CTA would not fit 200 KB
+    while (warps > 1 && cta_b + warps * warp_b > 200 * 1024) warps--;
+    const size_t smem = cta_b + warps * warp_b;
     GPRB_REQUIRE(smem <= 200 * 1024, "gprb_so3_power: nmax=%d lmax=%d needs %zu bytes of shared memory", nmax, lmax, smem);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[64] = {};
+    int dev = 0;
+    GPRB_CUDA(cudaGetDevice(&dev));
+    if (smem > 48 * 1024 && dev >= 0 && dev < 64 && smem > configured[dev]) {
         GPRB_CUDA(cudaFuncSetAttribute(so3_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[dev] = smem;
     }
-    so3_power_kernel<<<n_atoms, 128, smem, (cudaStream_t)stream>>>(a, p);
+    so3_power_kernel<<<n_atoms, warps * 32, smem, (cudaStream_t)stream>>>(a, p);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
     return GPRB_OK;
