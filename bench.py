@@ -639,8 +639,11 @@ def main():
         barrier()
         _lib.PROFILE = []
         t0 = time.perf_counter()
+        step_s = []
         for _ in range(args.steps):
+            t_s = time.perf_counter()
             res = e2e_step()
+            step_s.append(time.perf_counter() - t_s)      # (the call ends with a host synchronisation: gprb_lml_eval reads its scalars back)
         barrier()
         dt = (time.perf_counter() - t0) / args.steps
         prof, _lib.PROFILE = _lib.PROFILE, None
@@ -653,11 +656,12 @@ def main():
             parts[n] = parts.get(n, 0.0) + a.elapsed_time(b) / args.steps
             host_parts[n] = host_parts.get(n, 0.0) + h * 1e3 / args.steps
         # device -> host reads of a step: 2 doubles per scalar-reducing call, the potrf status word
-        scalar_calls = sum(1 for n, _, _, _ in prof if n.startswith(("gprb_lml_", "gprb_w_block_sum")))
-        d2h = (16 * scalar_calls + 4 * sum(1 for n, _, _, _ in prof if n == "gprb_chol_factor")) / args.steps
+        # device -> host reads of a step: gprb_lml_eval copies 9 doubles + 2 status words back, once
+        d2h = 80 * sum(1 for n, _, _, _ in prof if n == "gprb_lml_eval") / args.steps
         lml, grad = res
         result["e2e"] = {"value": flops / dt * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
                          "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
+                         "ms_per_step_min_max_on_rank0": [min(step_s) * 1e3, max(step_s) * 1e3],
                          "call": "GP.log_marginal_likelihood(theta, eval_gradient=True) from pinned host packed arrays",
                          "device_ms_by_entry_point": {k: round(v, 3) for k, v in sorted(parts.items())},
                          "host_ms_inside_entry_point": {k: round(v, 3) for k, v in sorted(host_parts.items())},

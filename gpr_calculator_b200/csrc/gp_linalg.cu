@@ -496,7 +496,8 @@ extern "C" int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const dou
 //   4 1/2 sum W_ii 2 noise_i, 5 1/2 sum of W over the held energy rows x all energy columns (want_s0, Dot sigma0 term).
 extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const double *y, double noise_e, double noise_f,
                              const double *dK_rows, long long lddk, int n_ranges, const int *ranges_host,
-                             int want_grad, int want_s0, int parts, double *alpha, double *out_host, void *stream) {
+                             int want_grad, int want_s0, int parts, double *alpha, double *work, long long work_doubles,
+                             double *out_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(K && y && alpha && out_host && N > 0 && NE >= 0 && NE <= N && ldk >= N, "gprb_lml_eval: bad argument");
     GPRB_REQUIRE(n_ranges >= 0 && (n_ranges == 0 || ranges_host), "gprb_lml_eval: bad row ranges");
@@ -519,13 +520,17 @@ extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const doub
     if (want_grad) {
         if (parts < 1) parts = 16;
         const double we = noise_e * noise_e, wf = noise_f * noise_f, we2 = 2.0 * noise_e, wf2 = 2.0 * noise_f;
+        const int blk = std::max(512, (N + parts - 1) / parts);
+        // the K^-1 slabs live in the caller's workspace ([NE + blk, N] doubles, gprb_lml_eval_work): large buffers that come and go
+        // fragment the stream-ordered pool the packs are allocated from (measured: occasional 1-2 s stalls of the next pack creation)
+        GPRB_REQUIRE(work && work_doubles >= (long long)(NE + std::min(blk, N)) * N, "gprb_lml_eval: workspace of %lld doubles needed",
+                     (long long)(NE + std::min(blk, N)) * N);
         double *Einv = nullptr;
+        double *slab_buf = work + (size_t)NE * N;
         if (NE) {
-            Einv = (double *)scratch.get((size_t)NE * N * sizeof(double));
-            if (!Einv) return GPRB_ERR_CUDA;
+            Einv = work;
             if ((rc = inverse_rows_enqueue(K, ldk, N, 0, NE, 0, Einv, N, st))) return rc;
         }
-        const int blk = std::max(512, (N + parts - 1) / parts);
         long long off = 0;                                   // first row of the range inside dK_rows
         for (int q = 0; q < n_ranges; q++) {
             const int R0 = ranges_host[2 * q], R1 = ranges_host[2 * q + 1];
@@ -534,24 +539,20 @@ extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const doub
             while (a < R1) {
                 int b;
                 const double *rows; long long ldr; int c0;
-                void *slab = nullptr;
                 if (a < NE) {                                 // energy rows: a slice of K^-1[0:NE, :]
                     b = std::min(R1, NE);
                     rows = Einv + (size_t)a * N; ldr = N; c0 = 0;
-                } else {
+                } else {                                      // stream order: the previous block's trace has read the slab
                     b = std::min(R1, a + blk);
                     c0 = a; ldr = N - c0;
-                    GPRB_CUDA(cudaMallocAsync(&slab, (size_t)(b - a) * ldr * sizeof(double), st));
-                    rc = inverse_rows_enqueue(K, ldk, N, a, b, c0, (double *)slab, ldr, st);
-                    if (rc) { gprb_pool_free(slab, st); return rc; }
-                    rows = (const double *)slab;
+                    if ((rc = inverse_rows_enqueue(K, ldk, N, a, b, c0, slab_buf, ldr, st))) return rc;
+                    rows = slab_buf;
                 }
                 const double *dptr = dK_rows ? dK_rows + (off + (a - R0)) * lddk : nullptr;
                 rc = trace_enqueue(N, a, b, alpha, virtual_base(rows, ldr, a, c0), ldr, dptr, lddk, NE, we, wf, we2, wf2, 2,
                                    Einv, N, acc + 2, 1, scratch, st);
                 if (!rc && want_s0 && b <= NE)
                     rc = block_sum_enqueue(N, a, b, 0, NE, alpha, Einv, N, acc + 5, 1, scratch, st);
-                gprb_pool_free(slab, st);                     // stream-ordered: released after the trace has read it
                 if (rc) return rc;
                 a = b;
             }
@@ -567,6 +568,13 @@ extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const doub
     out_host[0] = hacc[0]; out_host[1] = hacc[1]; out_host[2] = hacc[2]; out_host[3] = hacc[3]; out_host[4] = hacc[4];
     out_host[5] = hacc[5];
     return GPRB_OK;
+}
+
+extern "C" long long gprb_lml_eval_work(int N, int NE, int want_grad, int parts) {
+    if (!want_grad || N <= 0) return 0;
+    if (parts < 1) parts = 16;
+    const int blk = std::max(512, (N + parts - 1) / parts);
+    return (long long)(NE + std::min(blk, N)) * N;
 }
 
 // one CTA per test row, half-product variant: W = Ks . triu(Kinv) (trmm), k^T Kinv k = sum_j k_j (2 W_j - Kinv_jj k_j)

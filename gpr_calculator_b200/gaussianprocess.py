@@ -444,9 +444,12 @@ class GP():
         out = (ctypes_double * 8)()
         flat = [int(v) for r in r_ranges for v in r]
         ranges = (ctypes.c_int * max(len(flat), 1))(*flat)
+        parts = int(os.environ.get("GPRB_INVERSE_ROW_PARTS", "16"))
+        n_work = int(_lib.load().gprb_lml_eval_work(N, NE, int(bool(want_grad)), parts))
+        work = torch.empty(max(n_work, 1), dtype=F64, device="cuda")        # torch's caching allocator keeps it across evaluations
         _lib.call("gprb_lml_eval", ptr(K), K.stride(0), N, NE, ptr(y), float(noise_e), float(noise_f),
                   ptr(dK), dK.stride(0) if dK is not None else N, len(r_ranges), ranges, int(bool(want_grad)),
-                  int(bool(want_s0)), int(os.environ.get("GPRB_INVERSE_ROW_PARTS", "16")), ptr(alpha), out, stream())
+                  int(bool(want_s0)), parts, ptr(alpha), ptr(work), n_work, out, stream())
         return alpha, [float(v) for v in out]
 
     def _lml_gradient_full_inverse(self, K, alpha, dK, r_ranges, N, NE, noise_e, noise_f, is_rbf):

@@ -198,10 +198,14 @@ int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const double *alpha_
  *   out_host[8]: [0] sum_i log L_ii, [1] y.alpha, [2] 1/2 tr(W dK) over the held rows, [3] 1/2 sum W_ii noise_i^2,
  *     [4] 1/2 sum W_ii 2 noise_i, [5] 1/2 sum of W over (held energy rows) x (all energy columns) when want_s0
  *     (the Dot kernel's d/dsigma0 term, dot_kernel.py:58).  Sharded callers all-reduce [2..5].
- * Returns GPRB_ERR_LINALG when K is not positive definite (gaussianprocess.py:174-177). */
+ * Returns GPRB_ERR_LINALG when K is not positive definite (gaussianprocess.py:174-177).
+ *   work_dev: caller-owned workspace of gprb_lml_eval_work(N, NE, want_grad, parts) doubles (the K^-1 slabs of one block of rows
+ *     and of the energy rows; may be NULL when want_grad = 0). */
 int gprb_lml_eval(double *K_dev, long long ldk, int N, int NE, const double *y_dev, double noise_e, double noise_f,
                   const double *dK_rows_dev, long long lddk, int n_ranges, const int *ranges_host,
-                  int want_grad, int want_s0, int parts, double *alpha_dev, double *out_host, void *stream);
+                  int want_grad, int want_s0, int parts, double *alpha_dev, double *work_dev, long long work_doubles,
+                  double *out_host, void *stream);
+long long gprb_lml_eval_work(int N, int NE, int want_grad, int parts);
 /* mean[i] = Ks[i,:].alpha ;  if var_dev: var[i] = max(diag[i] - Ks[i,:] Kinv Ks[i,:]^T, 0)
  * (cuBLAS DGEMM + fused row reduction; gaussianprocess.py:880, 904-908).  work_dev: [m, N] scratch. */
 int gprb_predict(int m, int N, const double *Ks_dev, long long ldks, const double *alpha_dev,
