@@ -55,8 +55,10 @@ SIGNATURES = {
     "gprb_transpose_copy": (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_vp]),
     "gprb_fp64_dmma_peak": (c_int, [c_vp, c_vp]),
     "gprb_w_block_sum": (c_int, [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_ll, c_vp, c_vp]),
-    "gprb_lml_eval": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_dbl, c_dbl, c_vp, c_ll, c_int, c_vp, c_int, c_int, c_int,
+    "gprb_lml_eval": (c_int, [c_vp, c_ll, c_int, c_int, c_vp, c_dbl, c_dbl, c_vp, c_ll, c_int, c_vp, c_int, c_int, c_int, c_int,
                              c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "gprb_chol_panel": (c_int, [c_vp, c_ll, c_int, c_int, c_int, c_vp, c_vp]),
+    "gprb_chol_trailing": (c_int, [c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "gprb_lml_eval_work": (c_ll, [c_int, c_int, c_int, c_int]),
     "gprb_predict": (c_int, [c_int, c_int, c_vp, c_ll, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gprb_predict_chol": (c_int, [c_int, c_int, c_vp, c_ll, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -496,8 +496,8 @@ extern "C" int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const dou
 //   4 1/2 sum W_ii 2 noise_i, 5 1/2 sum of W over the held energy rows x all energy columns (want_s0, Dot sigma0 term).
 extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const double *y, double noise_e, double noise_f,
                              const double *dK_rows, long long lddk, int n_ranges, const int *ranges_host,
-                             int want_grad, int want_s0, int parts, double *alpha, double *work, long long work_doubles,
-                             double *out_host, void *stream) {
+                             int want_grad, int want_s0, int parts, int prefactored, double *alpha, double *work,
+                             long long work_doubles, double *out_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     GPRB_REQUIRE(K && y && alpha && out_host && N > 0 && NE >= 0 && NE <= N && ldk >= N, "gprb_lml_eval: bad argument");
     GPRB_REQUIRE(n_ranges >= 0 && (n_ranges == 0 || ranges_host), "gprb_lml_eval: bad row ranges");
@@ -509,14 +509,23 @@ extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const doub
     double *acc = (double *)scratch.get(9 * sizeof(double));      // [0..1] lml terms, [2..4] traces, [5..7] sigma0 block sum
     if (!info || !acc) return GPRB_ERR_CUDA;
     GPRB_CUDA(cudaMemsetAsync(acc, 0, 9 * sizeof(double), st));
-    add_noise_kernel<<<(N + 255) / 256, 256, 0, st>>>(K, ldk, N, NE, noise_e * noise_e, noise_f * noise_f);
-    GPRB_LAUNCHED();
-    if ((rc = factor_enqueue(K, ldk, N, info, scratch, st))) return rc;
+    GPRB_CUDA(cudaMemsetAsync(info, 0, 2 * sizeof(int), st));
+    // device time of the two phases (factor + alpha, gradient solves + traces): out_host[6], out_host[7] in ms
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int k = 0; k < 3; k++) if (e[k]) cudaEventDestroy(e[k]); } } ev_guard{ev};
+    for (int k = 0; k < 3; k++) GPRB_CUDA(cudaEventCreate(&ev[k]));
+    GPRB_CUDA(cudaEventRecord(ev[0], st));
+    if (!prefactored) {      // prefactored: K already holds the factor of K + noise in its row-major lower triangle (multi-GPU Cholesky)
+        add_noise_kernel<<<(N + 255) / 256, 256, 0, st>>>(K, ldk, N, NE, noise_e * noise_e, noise_f * noise_f);
+        GPRB_LAUNCHED();
+        if ((rc = factor_enqueue(K, ldk, N, info, scratch, st))) return rc;
+    }
     GPRB_CUDA(cudaMemcpyAsync(alpha, y, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if ((rc = solve_vec_enqueue(K, ldk, N, alpha, info + 1))) return rc;
     lml_terms_kernel<<<1, 1024, 0, st>>>(K, ldk, N, y, alpha, acc);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
+    GPRB_CUDA(cudaEventRecord(ev[1], st));
     if (want_grad) {
         if (parts < 1) parts = 16;
         const double we = noise_e * noise_e, wf = noise_f * noise_f, we2 = 2.0 * noise_e, wf2 = 2.0 * noise_f;
@@ -559,6 +568,7 @@ extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const doub
             off += R1 - R0;
         }
     }
+    GPRB_CUDA(cudaEventRecord(ev[2], st));
     double hacc[9];
     int hinfo[2] = {-1, -1};
     GPRB_CUDA(cudaMemcpyAsync(hacc, acc, sizeof hacc, cudaMemcpyDeviceToHost, st));
@@ -567,6 +577,10 @@ extern "C" int gprb_lml_eval(double *K, long long ldk, int N, int NE, const doub
     if (hinfo[0] != 0) { gprb_set_error("matrix not positive definite (potrf info = %d)", hinfo[0]); return GPRB_ERR_LINALG; }
     out_host[0] = hacc[0]; out_host[1] = hacc[1]; out_host[2] = hacc[2]; out_host[3] = hacc[3]; out_host[4] = hacc[4];
     out_host[5] = hacc[5];
+    float ms01 = 0.f, ms12 = 0.f;
+    cudaEventElapsedTime(&ms01, ev[0], ev[1]);
+    cudaEventElapsedTime(&ms12, ev[1], ev[2]);
+    out_host[6] = ms01; out_host[7] = ms12;
     return GPRB_OK;
 }
 
@@ -677,6 +691,64 @@ extern "C" int gprb_predict_chol(int m, int N, const double *Ks, long long ldks,
     predict_rows_chol_kernel<<<m, 256, 0, st>>>(N, Ks, ldks, alpha, work, diag, mean, var);
     GPRB_LAUNCHED();
     GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+namespace {
+// *acc = first failing global row (1-based, potrf convention) over a sequence of panel factorisations
+__global__ void accumulate_info_kernel(const int *info, int k0, int *acc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && *info != 0 && *acc == 0) *acc = *info > 0 ? k0 + *info : *info;
+}
+}  // namespace
+
+// ---- building blocks of the multi-GPU right-looking Cholesky (GP._distributed_cholesky, dist.py) -------------------
+// K is the row-major symmetric matrix (every rank holds a full copy); the factor L (K = L L^T) ends in the row-major lower
+// triangle, panel by panel.  gprb_chol_panel (owner of block column k): L_kk = chol(A_kk) (cuSOLVER potrf on the nb x nb block),
+// then the rows below, L_ik = A_ik L_kk^-T (one cuBLAS trsm).  info_dev accumulates the first failing row (0 = ok); no host
+// synchronisation.  gprb_chol_trailing (owner of block column j > k): A[j0:N, j0:j0+nbj] -= L[j0:N, k0:k0+nbk] L[j0:j0+nbj, k0:k0+nbk]^T.
+extern "C" int gprb_chol_panel(double *K, long long ldk, int N, int k0, int nbk, int *info_dev, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(K && info_dev && N > 0 && 0 <= k0 && nbk > 0 && k0 + nbk <= N, "gprb_chol_panel: bad argument");
+    int rc = handles(st);
+    if (rc) return rc;
+    double *Akk = K + (long long)k0 * ldk + k0;
+    Scratch scratch(st);
+    int lwork = 0;
+    if (cusolverDnDpotrf_bufferSize(g_solver, FACTOR_UPLO, nbk, Akk, (int)ldk, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+        gprb_set_error("potrf_bufferSize failed"); return GPRB_ERR_CUDA;
+    }
+    double *work = (double *)scratch.get((size_t)(lwork > 0 ? lwork : 1) * sizeof(double));
+    int *info = (int *)scratch.get(sizeof(int));
+    if (!work || !info) return GPRB_ERR_CUDA;
+    if (cusolverDnDpotrf(g_solver, FACTOR_UPLO, nbk, Akk, (int)ldk, work, lwork, info) != CUSOLVER_STATUS_SUCCESS) {
+        gprb_set_error("cusolverDnDpotrf (panel) failed"); return GPRB_ERR_CUDA;
+    }
+    accumulate_info_kernel<<<1, 32, 0, st>>>(info, k0, info_dev);
+    GPRB_LAUNCHED();
+    const int m = N - (k0 + nbk);
+    if (m > 0) {
+        // column-major view: X^T (nbk x m) = (U^T)^-1 A_ik^T with U = L_kk^T in the upper triangle of the block
+        const double one = 1.0;
+        cublasStatus_t bs = cublasDtrsm_64(g_blas, CUBLAS_SIDE_LEFT, FACTOR_UPLO, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int64_t)nbk, (int64_t)m,
+                                           &one, Akk, (int64_t)ldk, K + (long long)(k0 + nbk) * ldk + k0, (int64_t)ldk);
+        if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDtrsm_64 (panel) status %d", (int)bs); return GPRB_ERR_CUDA; }
+    }
+    GPRB_CUDA(cudaGetLastError());
+    return GPRB_OK;
+}
+
+extern "C" int gprb_chol_trailing(double *K, long long ldk, int N, int k0, int nbk, int j0, int nbj, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GPRB_REQUIRE(K && N > 0 && 0 <= k0 && nbk > 0 && k0 + nbk <= j0 && nbj > 0 && j0 + nbj <= N, "gprb_chol_trailing: bad argument");
+    int rc = handles(st);
+    if (rc) return rc;
+    // row-major C [m x nbj] -= A [m x nbk] B^T, B = the first nbj rows of A; column-major view: C^T (nbj x m) -= B_cm^T A_cm
+    const double minus = -1.0, one = 1.0;
+    const long long m = N - j0;
+    const double *A = K + (long long)j0 * ldk + k0;
+    cublasStatus_t bs = cublasDgemm_64(g_blas, CUBLAS_OP_T, CUBLAS_OP_N, (int64_t)nbj, (int64_t)m, (int64_t)nbk, &minus, A, (int64_t)ldk, A,
+                                       (int64_t)ldk, &one, K + (long long)j0 * ldk + j0, (int64_t)ldk);
+    if (bs != CUBLAS_STATUS_SUCCESS) { gprb_set_error("cublasDgemm_64 (trailing update) status %d", (int)bs); return GPRB_ERR_CUDA; }
     return GPRB_OK;
 }
 

@@ -171,6 +171,45 @@ def all_to_all_rows(out, inp, recv_rows, send_rows, group=None):
     return out
 
 
+def distributed_cholesky(K, nb=1024, group=None):
+    """In-place Cholesky factorisation K = L L^T of a symmetric matrix that EVERY rank holds in full (row-major [N, N] CUDA
+    tensor; on return the row-major lower triangle of every rank's copy holds L, the strict upper triangle is undefined).
+
+    Right-looking blocked algorithm, block column k of the lower triangle owned by rank k mod G: the owner factors the
+    diagonal block and solves for the rows below (gprb_chol_panel: cuSOLVER potrf + cuBLAS trsm), the finished panel is
+    broadcast over NVLink (NCCL) into every copy, and every rank applies the rank-nb update to the block columns it owns
+    (gprb_chol_trailing: one cuBLAS gemm per column).  All steps are stream ordered; one host synchronisation at the end
+    reads the status.  Replaces the factorisation the reference repeats on every MPI rank (gaussianprocess.py:174): with G
+    ranks the N^3 / 3 flops are split G ways (S5 on 8 B200: 0.36 s replicated -> see DESIGN.md).
+    Returns potrf's info (0 = positive definite), identical on every rank."""
+    from . import _lib
+    from .device import ptr, stream
+    rank, size = world()
+    N = int(K.shape[0])
+    ld = int(K.stride(0))
+    info = torch.zeros(1, dtype=torch.int32, device=K.device)
+    st = stream()
+    nblk = -(-N // nb)
+    for k in range(nblk):
+        k0, nbk = k * nb, min(nb, N - k * nb)
+        owner = k % size
+        if owner == rank:
+            _lib.call("gprb_chol_panel", ptr(K), ld, N, k0, nbk, ptr(info), st)
+        if size > 1:
+            # the panel (rows k0..N of block column k) travels as one contiguous buffer
+            panel = K[k0:, k0:k0 + nbk]
+            buf = panel.contiguous() if owner == rank else torch.empty((N - k0, nbk), dtype=K.dtype, device=K.device)
+            dist.broadcast(buf, src=owner if group is None else dist.get_global_rank(group, owner), group=group)
+            if owner != rank:
+                panel.copy_(buf)
+        for j in range(k + 1, nblk):
+            if j % size == rank:
+                _lib.call("gprb_chol_trailing", ptr(K), ld, N, k0, nbk, j * nb, min(nb, N - j * nb), st)
+    if size > 1:
+        dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
+    return int(info.item())
+
+
 def all_reduce_array(values, device="cpu", group=None):
     """Element-wise sum of a 1-D float64 numpy array over ranks (sharded prediction: every rank fills its own slots of a
     zero array, so the sum is an exact gather)."""

@@ -371,6 +371,13 @@ class GP():
         MLL = -0.5 * ya - logdet - N / 2 * np.log(2 * np.pi)
         if not eval_gradient:
             return self._sync_ranks(MLL)
+        if getattr(self, "_inverse_cost", None) is not None and gdist.world()[1] > 1:
+            # re-balance the inverse-rows windows: share of rank r ~ (cost it handled) / (time its solves took), damped
+            rates = np.asarray(gdist.all_gather_floats(self._inverse_cost / max(out[7], 1e-3), device="cuda"))
+            if np.all(rates > 0):
+                used = self._inverse_speed_used
+                self._inverse_speed = 0.5 * used / used.sum() + 0.5 * rates / rates.sum()
+            self._inverse_cost = None
         if full_inverse:
             g_l, half_w_noise, half_w_base, g_s0 = self._lml_gradient_full_inverse(K, alpha, dK, r_ranges, N, NE, noise_e,
                                                                                     noise_f, is_rbf)
@@ -402,7 +409,15 @@ class GP():
         (e0, e1), (r0, r1) = r_ranges
         NF = (N - NE) // 3
         first = NE + 3 * np.arange(NF, dtype=np.float64)
-        bounds = gdist.split_groups(3.0 * (N - first) ** 2, size)
+        cost = 3.0 * (N - first) ** 2
+        # shares follow the measured solve throughput of the ranks (every block of rows also carries a fixed latency of two
+        # triangular solves, which the flop model does not see): updated after every evaluation, identical on all ranks
+        speed = getattr(self, "_inverse_speed", None)
+        if speed is None or len(speed) != size:
+            speed = np.ones(size)
+        bounds = gdist.split_groups(cost, size, speed=speed)
+        self._inverse_cost = float(cost[bounds[rank]:bounds[rank + 1]].sum())
+        self._inverse_speed_used = speed
         f_old = gdist.all_gather_floats(float((r0 - NE) // 3), device="cuda") + [float(NF)]
         f_old = [int(v) for v in f_old]                      # force windows of the build, by rank (contiguous, ordered)
         # sanity: the build's windows tile [0, NF)
@@ -445,11 +460,19 @@ class GP():
         flat = [int(v) for r in r_ranges for v in r]
         ranges = (ctypes.c_int * max(len(flat), 1))(*flat)
         parts = int(os.environ.get("GPRB_INVERSE_ROW_PARTS", "16"))
+        # several GPUs: the factorisation is shared by the ranks (dist.distributed_cholesky) instead of repeated on each
+        prefactored = 0
+        if gdist.world()[1] > 1 and N >= self.DIST_CHOLESKY_MIN_N and os.environ.get("GPRB_DIST_CHOLESKY", "1") not in ("", "0"):
+            _lib.call("gprb_add_noise", ptr(K), K.stride(0), N, NE, float(noise_e), float(noise_f), stream())
+            info = gdist.distributed_cholesky(K, nb=int(os.environ.get("GPRB_DIST_CHOLESKY_NB", "1024")))
+            if info != 0:
+                raise _lib.NotPositiveDefinite(_lib.ERR_LINALG, "matrix not positive definite (distributed potrf info = %d)" % info)
+            prefactored = 1
         n_work = int(_lib.load().gprb_lml_eval_work(N, NE, int(bool(want_grad)), parts))
         work = torch.empty(max(n_work, 1), dtype=F64, device="cuda")        # torch's caching allocator keeps it across evaluations
         _lib.call("gprb_lml_eval", ptr(K), K.stride(0), N, NE, ptr(y), float(noise_e), float(noise_f),
                   ptr(dK), dK.stride(0) if dK is not None else N, len(r_ranges), ranges, int(bool(want_grad)),
-                  int(bool(want_s0)), parts, ptr(alpha), ptr(work), n_work, out, stream())
+                  int(bool(want_s0)), parts, prefactored, ptr(alpha), ptr(work), n_work, out, stream())
         return alpha, [float(v) for v in out]
 
     def _lml_gradient_full_inverse(self, K, alpha, dK, r_ranges, N, NE, noise_e, noise_f, is_rbf):
@@ -590,6 +613,7 @@ class GP():
     # forces one route; variance_route_probe() reports how far the two are apart on the current model.
     CHOL_VARIANCE_MIN_ROWS = 512
     PROBE_ROWS = 128
+    DIST_CHOLESKY_MIN_N = 8192          # below this the panels are too small to pay for their broadcasts
 
     def variance_route_probe(self, K_trans, diag):
         """max |sigma_chol - sigma_inverse| over the first PROBE_ROWS rows of K*: a direct estimate of the conditioning

@@ -197,15 +197,27 @@ int gprb_w_block_sum(int N, int r0, int r1, int c0, int c1, const double *alpha_
  *   alpha_dev[N] receives alpha; K_dev holds the factor on return.
  *   out_host[8]: [0] sum_i log L_ii, [1] y.alpha, [2] 1/2 tr(W dK) over the held rows, [3] 1/2 sum W_ii noise_i^2,
  *     [4] 1/2 sum W_ii 2 noise_i, [5] 1/2 sum of W over (held energy rows) x (all energy columns) when want_s0
- *     (the Dot kernel's d/dsigma0 term, dot_kernel.py:58).  Sharded callers all-reduce [2..5].
+ *     (the Dot kernel's d/dsigma0 term, dot_kernel.py:58).  Sharded callers all-reduce [2..5].  [6], [7]: device milliseconds
+ *     of the factor + alpha phase and of the gradient phase (solves + traces) of this call.
  * Returns GPRB_ERR_LINALG when K is not positive definite (gaussianprocess.py:174-177).
+ *   prefactored != 0: K_dev already holds the factor of K + noise in its row-major lower triangle (the multi-GPU Cholesky below);
+ *     noise and potrf are skipped.
  *   work_dev: caller-owned workspace of gprb_lml_eval_work(N, NE, want_grad, parts) doubles (the K^-1 slabs of one block of rows
  *     and of the energy rows; may be NULL when want_grad = 0). */
 int gprb_lml_eval(double *K_dev, long long ldk, int N, int NE, const double *y_dev, double noise_e, double noise_f,
                   const double *dK_rows_dev, long long lddk, int n_ranges, const int *ranges_host,
-                  int want_grad, int want_s0, int parts, double *alpha_dev, double *work_dev, long long work_doubles,
-                  double *out_host, void *stream);
+                  int want_grad, int want_s0, int parts, int prefactored, double *alpha_dev, double *work_dev,
+                  long long work_doubles, double *out_host, void *stream);
 long long gprb_lml_eval_work(int N, int NE, int want_grad, int parts);
+/* Building blocks of the multi-GPU right-looking Cholesky (every rank holds a full row-major copy of K + noise; block column k
+ * of the lower triangle is owned by rank k mod G; dist.distributed_cholesky broadcasts each finished panel to all ranks):
+ *   gprb_chol_panel    (owner of k): L_kk = chol(A_kk) (cuSOLVER potrf, nbk x nbk), then L_ik = A_ik L_kk^-T for the rows below
+ *                      (one cuBLAS trsm); *info_dev keeps the first failing row (0 = positive definite so far); no host sync.
+ *   gprb_chol_trailing (owner of j > k): A[j0:N, j0:j0+nbj] -= L[j0:N, k0:k0+nbk] L[j0:j0+nbj, k0:k0+nbk]^T (one cuBLAS gemm).
+ * Replaces the replicated scipy cholesky of gaussianprocess.py:174 on every MPI rank. */
+int gprb_chol_panel(double *K_dev, long long ldk, int N, int k0, int nbk, int *info_dev, void *stream);
+int gprb_chol_trailing(double *K_dev, long long ldk, int N, int k0, int nbk, int j0, int nbj, void *stream);
+
 /* mean[i] = Ks[i,:].alpha ;  if var_dev: var[i] = max(diag[i] - Ks[i,:] Kinv Ks[i,:]^T, 0)
  * (cuBLAS DGEMM + fused row reduction; gaussianprocess.py:880, 904-908).  work_dev: [m, N] scratch. */
 int gprb_predict(int m, int N, const double *Ks_dev, long long ldks, const double *alpha_dev,

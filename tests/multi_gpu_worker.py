@@ -45,9 +45,12 @@ def main():
     scale = float(K1.abs().max())
 
     results = {}
-    for mode in ("peer", "nccl", "fullinv"):
+    for mode in ("peer", "nccl", "fullinv", "distchol"):
         os.environ["GPRB_NO_PEER"] = "1" if mode == "nccl" else "0"
         os.environ["GPRB_FULL_INVERSE"] = "1" if mode == "fullinv" else "0"     # potri on every rank instead of inverse rows
+        # "distchol": the factorisation shared by the ranks (dist.distributed_cholesky, panels of 256 rows) instead of repeated on each
+        GP.DIST_CHOLESKY_MIN_N = 512 if mode == "distchol" else 10 ** 9
+        os.environ["GPRB_DIST_CHOLESKY_NB"] = "256"
         gp = make_gp()
         for it in range(3):            # repeated builds re-use (and re-zero) the peer-mapped matrix
             K, dK, ranges = gp._build_K(grad=True)
@@ -88,6 +91,8 @@ def main():
     # single-GPU LML on rank-local unsharded algebra: same GP code with world pretending 1 is not possible
     # inside a process group, so compare the two sharded paths with each other and K with the unsharded build
     lml_f, g_f = results["fullinv"][3], results["fullinv"][4]
+    lml_d, g_d = results["distchol"][3], results["distchol"][4]
+    GP.DIST_CHOLESKY_MIN_N = 512          # the fit / prediction checks below run on the shared factorisation too
     # Dot kernel: the d/dsigma0 term of the sharded gradient against the potri route
     from gpr_calculator_b200.kernels import Dot_mb
     dot = {}
@@ -123,9 +128,11 @@ def main():
               % (pred_err, same_theta, gpp.kernel.parameters()), flush=True)
     ok = (pred_ok and results["peer"][1] <= 1e-12 and results["nccl"][1] <= 1e-12 and results["peer"][2] <= 1e-12 and same
           and abs(lml_p - lml_n) <= 1e-9 * abs(lml_n) and np.allclose(g_p, g_n, rtol=1e-9, atol=1e-9)
-          and abs(lml_p - lml_f) <= 1e-9 * abs(lml_f) and np.allclose(g_p, g_f, rtol=1e-7, atol=1e-7) and dot_ok)
+          and abs(lml_p - lml_f) <= 1e-9 * abs(lml_f) and np.allclose(g_p, g_f, rtol=1e-7, atol=1e-7) and dot_ok
+          and abs(lml_p - lml_d) <= 1e-10 * abs(lml_p) and np.allclose(g_p, g_d, rtol=1e-8, atol=1e-8))
     if rank == 0:
-        print("gradient rows %s | potri %s ; Dot rows %s | potri %s" % (g_p, g_f, dot["rows"], dot["fullinv"]), flush=True)
+        print("gradient rows %s | potri %s | shared Cholesky %s (lml %.12g vs %.12g); Dot rows %s | potri %s"
+              % (g_p, g_f, g_d, lml_d, lml_p, dot["rows"], dot["fullinv"]), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     print("[rank %d/%d] N=%d K err peer %.2e nccl %.2e dK err %.2e bitwise(peer,nccl)=%s lml %.9f / %.9f grad %s / %s"

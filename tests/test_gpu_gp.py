@@ -485,3 +485,23 @@ def test_cur_selection_vs_reference(gsel):
         sure = set(np.flatnonzero(omega > cut + 1e-6))
         assert sure <= set(int(i) for i in sel_f) and sure <= set(int(i) for i in ref_f)
         assert np.all(omega[sel_f] >= cut - 1e-6)
+
+
+def test_blocked_cholesky_single_rank():
+    """dist.distributed_cholesky on one rank is a plain right-looking blocked Cholesky (gprb_chol_panel + gprb_chol_trailing):
+    factor against scipy, ragged last panel, and the status of a matrix that is not positive definite."""
+    import torch
+    from scipy.linalg import cholesky
+    from gpr_calculator_b200 import dist as gdist
+    rng = np.random.default_rng(31)
+    for N, nb in ((700, 128), (513, 512), (96, 1024)):
+        A = rng.normal(size=(N, N))
+        K = A @ A.T + N * np.eye(N)
+        Kd = torch.as_tensor(K, device="cuda").contiguous()
+        assert gdist.distributed_cholesky(Kd, nb=nb) == 0
+        L = np.tril(Kd.cpu().numpy())
+        assert rel_err(L, cholesky(K, lower=True)) <= 1e-12 and rel_err(L @ L.T, K) <= 1e-13
+    A = rng.normal(size=(700, 700))
+    K = A @ A.T + 700 * np.eye(700)
+    K[300, 300] = -1.0
+    assert gdist.distributed_cholesky(torch.as_tensor(K, device="cuda").contiguous(), nb=128) > 0
