@@ -171,7 +171,7 @@ def all_to_all_rows(out, inp, recv_rows, send_rows, group=None):
     return out
 
 
-def distributed_cholesky(K, nb=1024, group=None):
+def distributed_cholesky(K, nb=1024, group=None, panel_fn=None, trailing_fn=None):
     """In-place Cholesky factorisation K = L L^T of a symmetric matrix that EVERY rank holds in full (row-major [N, N] CUDA
     tensor; on return the row-major lower triangle of every rank's copy holds L, the strict upper triangle is undefined).
 
@@ -181,20 +181,28 @@ def distributed_cholesky(K, nb=1024, group=None):
     (gprb_chol_trailing: one cuBLAS gemm per column).  All steps are stream ordered; one host synchronisation at the end
     reads the status.  Replaces the factorisation the reference repeats on every MPI rank (gaussianprocess.py:174): with G
     ranks the N^3 / 3 flops are split G ways (S5 on 8 B200: 0.36 s replicated -> see DESIGN.md).
-    Returns potrf's info (0 = positive definite), identical on every rank."""
-    from . import _lib
-    from .device import ptr, stream
+    Returns potrf's info (0 = positive definite), identical on every rank.
+    panel_fn(K, k0, nbk, info) / trailing_fn(K, k0, nbk, j0, nbj): the two arithmetic steps; default = the library entry points
+    (the gloo test of the ownership / broadcast logic passes numpy stand-ins)."""
     rank, size = world()
     N = int(K.shape[0])
-    ld = int(K.stride(0))
     info = torch.zeros(1, dtype=torch.int32, device=K.device)
-    st = stream()
+    if panel_fn is None:
+        from . import _lib
+        from .device import ptr, stream
+        ld, st = int(K.stride(0)), stream()
+
+        def panel_fn(K, k0, nbk, info):
+            _lib.call("gprb_chol_panel", ptr(K), ld, N, k0, nbk, ptr(info), st)
+
+        def trailing_fn(K, k0, nbk, j0, nbj):
+            _lib.call("gprb_chol_trailing", ptr(K), ld, N, k0, nbk, j0, nbj, st)
     nblk = -(-N // nb)
     for k in range(nblk):
         k0, nbk = k * nb, min(nb, N - k * nb)
         owner = k % size
         if owner == rank:
-            _lib.call("gprb_chol_panel", ptr(K), ld, N, k0, nbk, ptr(info), st)
+            panel_fn(K, k0, nbk, info)
         if size > 1:
             # the panel (rows k0..N of block column k) travels as one contiguous buffer
             panel = K[k0:, k0:k0 + nbk]
@@ -204,7 +212,7 @@ def distributed_cholesky(K, nb=1024, group=None):
                 panel.copy_(buf)
         for j in range(k + 1, nblk):
             if j % size == rank:
-                _lib.call("gprb_chol_trailing", ptr(K), ld, N, k0, nbk, j * nb, min(nb, N - j * nb), st)
+                trailing_fn(K, k0, nbk, j * nb, min(nb, N - j * nb))
     if size > 1:
         dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
     return int(info.item())

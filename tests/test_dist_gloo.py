@@ -57,6 +57,25 @@ def _worker(rank, size, port, q):
     got_r = gd.all_to_all_rows(torch.empty((new_b[rank + 1] - new_b[rank], 4), dtype=torch.float64),
                                rows_all[old_b[rank]:old_b[rank + 1]].clone(), recv, send)
     ok = ok and bool(torch.equal(got_r, rows_all[new_b[rank]:new_b[rank + 1]]))
+    # shared Cholesky: ownership of the block columns, panel broadcasts and trailing updates with numpy stand-ins for the two
+    # library steps (gprb_chol_panel / gprb_chol_trailing); every rank must end with the full factor in its lower triangle
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(53, 53))
+    Kn = A @ A.T + 53 * np.eye(53)
+    Kt = torch.from_numpy(Kn.copy())
+
+    def panel(K, k0, nbk, info):
+        a = K.numpy()
+        L = np.linalg.cholesky(a[k0:k0 + nbk, k0:k0 + nbk])
+        a[k0:k0 + nbk, k0:k0 + nbk] = L
+        a[k0 + nbk:, k0:k0 + nbk] = np.linalg.solve(L, a[k0 + nbk:, k0:k0 + nbk].T).T
+
+    def trailing(K, k0, nbk, j0, nbj):
+        a = K.numpy()
+        a[j0:, j0:j0 + nbj] -= a[j0:, k0:k0 + nbk] @ a[j0:j0 + nbj, k0:k0 + nbk].T
+
+    info = gd.distributed_cholesky(Kt, nb=8, panel_fn=panel, trailing_fn=trailing)
+    ok = ok and info == 0 and bool(np.allclose(np.tril(Kt.numpy()), np.linalg.cholesky(Kn), rtol=0, atol=1e-12))
     s = gd.all_reduce_sum([float(rank + 1), 2.0])
     q.put((rank, ok, s, gd.world()))
     dist.destroy_process_group()
