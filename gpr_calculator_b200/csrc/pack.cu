@@ -35,66 +35,62 @@ extern "C" int gprb_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     return GPRB_OK;
 }
 
-// One CTA (8 warps) per tile of 8 consecutive flat rows; warp r prepares row r (rows >= n_rows are tail padding).
-// HBM-bound: reads 8*d*(1+ncols) bytes and writes 8*4ks*(1+ncols) per row.  The 8 rows of a tile are contiguous in x and in
-// dxdr and the tile's slab is contiguous in P, so the CTA reads both with block-wide coalesced loads into shared memory and
-// writes the finished slab (ncomp * ks * 256 B) back as one linear, fully coalesced copy.  (Round 1: one warp per row with
-// three strided passes over dxdr and 32-byte scattered stores: 2.6 TB/s = 39 % of the measured HBM bandwidth.)
-__global__ void __launch_bounds__(256) prep_rows_kernel(int n_padded, int n_rows, int d, int ncols, int ks, double norm_eps,
-                                                        const double *__restrict__ x, const double *__restrict__ dxdr,
-                                                        const int *__restrict__ ele,
-                                                        double *__restrict__ P, double *__restrict__ norm_out,
-                                                        int *__restrict__ elep, int *__restrict__ tile_rec) {
-    extern __shared__ double sh[];                    // [8][d] x | [8][d*ncols] dxdr | [ncomp*ks*32] slab
-    const int tile = blockIdx.x, tid = threadIdx.x, r = tid >> 5, lane = tid & 31;
-    const int ncomp = 1 + ncols, kp = 4 * ks;
-    double *sx = sh, *sdx = sx + 8 * d, *slab = sdx + 8 * d * ncols;
-    const int row0 = tile * 8;
-    const int nvalid = max(0, min(8, n_rows - row0));
-    for (int i = tid; i < nvalid * d; i += 256) sx[i] = x[(size_t)row0 * d + i];
-    for (int i = tid; i < nvalid * d * ncols; i += 256) sdx[i] = dxdr[(size_t)row0 * d * ncols + i];
-    for (int i = tid; i < ncomp * ks * 32; i += 256) slab[i] = 0.0;
-    __syncthreads();
-    const int row = row0 + r;
-    if (r < nvalid) {
-        const double *xr = sx + r * d;
-        double ss = 0.0;
-        for (int k = lane; k < d; k += 32) { double v = xr[k]; ss += v * v; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const double n = sqrt(ss) + norm_eps;
-        const bool dropped = (norm_eps == 0.0) && !(n > GPRB_EPS_NORM);
-        const double inv = dropped ? 0.0 : 1.0 / n;
-        // t_c = x^ . A[:,c]
-        double t[3] = {0.0, 0.0, 0.0};
-        const double *Ar = sdx + (size_t)r * d * ncols;
-        for (int c = 0; c < ncols; c++) {
-            double acc = 0.0;
-            for (int k = lane; k < d; k += 32) acc += (xr[k] * inv) * Ar[k * ncols + c];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            t[c] = acc;
-        }
-        for (int k = lane; k < d; k += 32) {
-            const int off = (k >> 2) * 32 + r * 4 + (k & 3);
-            const double xh = xr[k] * inv;
-            slab[off] = xh;
-            for (int c = 0; c < ncols; c++) slab[(c + 1) * ks * 32 + off] = dropped ? 0.0 : (Ar[k * ncols + c] - xh * t[c]) * inv;
-        }
-        if (lane == 0) {
-            norm_out[row] = n - norm_eps;
-            const int z = ele[row];
-            const int code = dropped ? -(z + 2) : z;
-            elep[row] = code;
-            tile_rec[(size_t)tile * GPRB_REC_INTS + r] = code;
-        }
-    } else if (lane == 0 && row < n_padded) {      // padding row
-        norm_out[row] = 0.0; elep[row] = -1; tile_rec[(size_t)tile * GPRB_REC_INTS + r] = -1;
-    }
-    __syncthreads();
+// One warp per row of the flat tile layout (rows >= n_rows are tail padding).
+// HBM-bound: reads 8*d*(1+ncols) bytes and writes 8*4ks*(1+ncols) per row.
+__global__ void prep_rows_kernel(int n_padded, int n_rows, int d, int ncols, int ks, double norm_eps,
+                                 const double *__restrict__ x, const double *__restrict__ dxdr,
+                                 const int *__restrict__ ele,
+                                 double *__restrict__ P, double *__restrict__ norm_out,
+                                 int *__restrict__ elep, int *__restrict__ tile_rec) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= n_padded) return;
+    const int ncomp = 1 + ncols;
+    const int tile = warp >> 3, r = warp & 7;
+    const int kp = 4 * ks;
+    const int src = warp < n_rows ? warp : -1;
     double *Pt = P + (size_t)tile * ncomp * ks * 32;
-    for (int i = tid; i < ncomp * ks * 32; i += 256) Pt[i] = slab[i];
-    (void)kp;
+    if (src < 0) {   // padding row
+        for (int c = 0; c < ncomp; c++)
+            for (int k = lane; k < kp; k += 32) Pt[((size_t)c * ks + (k >> 2)) * 32 + r * 4 + (k & 3)] = 0.0;
+        if (lane == 0) { norm_out[warp] = 0.0; elep[warp] = -1; tile_rec[(size_t)tile * GPRB_REC_INTS + r] = -1; }
+        return;
+    }
+    const double *xr = x + (size_t)src * d;
+    double ss = 0.0;
+    for (int k = lane; k < d; k += 32) { double v = xr[k]; ss += v * v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const double n = sqrt(ss) + norm_eps;
+    const bool dropped = (norm_eps == 0.0) && !(n > GPRB_EPS_NORM);
+    const double inv = dropped ? 0.0 : 1.0 / n;
+    // t_c = x^ . A[:,c]
+    double t[9];
+    const double *Ar = ncols ? dxdr + (size_t)src * d * ncols : nullptr;
+    for (int c = 0; c < ncols; c++) {
+        double acc = 0.0;
+        for (int k = lane; k < d; k += 32) acc += (xr[k] * inv) * Ar[(size_t)k * ncols + c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        t[c] = acc;
+    }
+    for (int k = lane; k < kp; k += 32) {
+        const size_t off = (size_t)(k >> 2) * 32 + r * 4 + (k & 3);
+        const double xh = (k < d) ? xr[k] * inv : 0.0;
+        Pt[off] = xh;
+        for (int c = 0; c < ncols; c++) {
+            double v = 0.0;
+            if (k < d && !dropped) v = (Ar[(size_t)k * ncols + c] - xh * t[c]) * inv;
+            Pt[(size_t)(c + 1) * ks * 32 + off] = v;
+        }
+    }
+    if (lane == 0) {
+        norm_out[warp] = n - norm_eps;
+        const int z = ele[src];
+        const int code = dropped ? -(z + 2) : z;
+        elep[warp] = code;
+        tile_rec[(size_t)tile * GPRB_REC_INTS + r] = code;
+    }
 }
 
 static bool is_device_ptr(const void *p) {
@@ -228,9 +224,10 @@ extern "C" int gprb_pack_create(gprb_pack **out, int n_groups, const int *group_
         (rc = stage_input(dxdr_any, ncols ? (size_t)rows * d * ncols : 0, &ddx, &odx, st)) ||
         (rc = stage_input(ele_any, (size_t)rows, &de, &oe, st))) { gprb_pack_destroy(p); return rc; }
     {
-        const size_t smem = (size_t)(8 * d * (1 + ncols) + p->ncomp * p->ks * 32) * sizeof(double);   // 16 KB for d = 30 force rows
-        prep_rows_kernel<<<tiles, 256, smem, st>>>(n_padded, p->n_rows, d, ncols, p->ks, norm_eps, dx, ddx, de,
-                                                   p->P, p->norm, p->elep, p->tile_rec);
+        const int threads = 256, wpb = threads / 32;
+        const int blocks = (n_padded + wpb - 1) / wpb;
+        prep_rows_kernel<<<blocks, threads, 0, st>>>(n_padded, p->n_rows, d, ncols, p->ks, norm_eps, dx, ddx, de,
+                                                     p->P, p->norm, p->elep, p->tile_rec);
         GPRB_LAUNCHED();
         PK_CUDA(cudaGetLastError());
     }
