@@ -237,7 +237,16 @@ class GP():
         n_loc = (e1 - e0) + 3 * (f1 - f0)
         peer = self._peer_matrix(N)
         K = peer.tensor if peer is not None else torch.empty((N, N), dtype=F64, device="cuda")
-        dK = torch.zeros((n_loc, N), dtype=F64, device="cuda") if has_dk else None
+        dK = None
+        if has_dk:
+            # one buffer with headroom for the whole optimisation: the adaptive windows change n_loc from build to build, and a
+            # fresh multi-GB allocation per build (no cached block of exactly that size) costs tens of milliseconds
+            buf = getattr(self, "_dK_buf", None)
+            if buf is None or buf.shape[1] != N or buf.shape[0] < n_loc:
+                self._dK_buf = buf = None
+                buf = self._dK_buf = torch.empty((min(N, int(1.25 * n_loc) + 64), N), dtype=F64, device="cuda")
+            dK = buf[:n_loc]
+            dK.zero_()
         ff = dict(use_tol=args.pop("use_tol"), tol=args.pop("tol"), zeta_ff=args.pop("zeta_ff"))
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if peer is not None:
@@ -427,7 +436,12 @@ class GP():
         send = [3 * max(0, min(f_old[rank + 1], bounds[d + 1]) - max(f_old[rank], bounds[d])) for d in range(size)]
         recv = [3 * max(0, min(f_old[s_ + 1], bounds[rank + 1]) - max(f_old[s_], bounds[rank])) for s_ in range(size)]
         g0, g1 = bounds[rank], bounds[rank + 1]
-        new = torch.empty((ne_loc + 3 * (g1 - g0), N), dtype=F64, device="cuda")
+        n_new = ne_loc + 3 * (g1 - g0)
+        buf = getattr(self, "_dK_inv_buf", None)          # reused across evaluations, like the build's buffer (_build_K)
+        if buf is None or buf.shape[1] != N or buf.shape[0] < n_new:
+            self._dK_inv_buf = buf = None
+            buf = self._dK_inv_buf = torch.empty((min(N, int(1.25 * n_new) + 64), N), dtype=F64, device="cuda")
+        new = buf[:n_new]
         if ne_loc:
             new[:ne_loc] = dK[:ne_loc]
         gdist.all_to_all_rows(new[ne_loc:], dK[ne_loc:], recv, send)
