@@ -1,4 +1,5 @@
-"""Lane-level numpy emulation of the two-stage K_ff contraction proposed in README.md (not built).
+"""Lane-level numpy emulation of the two-stage K_ff contraction (csrc/cov_mma.cu, TWO path: the default no-gradient K_ff kernel;
+run as a CPU test by tests/test_host_logic.py::test_two_stage_contraction_emulation).
 
 Checks, with the register layouts of mma.sync.m8n8k4.f64 on sm_100a
     A fragment: lane holds A[row = lane // 4][k = lane % 4]

@@ -355,3 +355,25 @@ def test_gpr_calc_import_alias():
             "assert GP is g.GP and SO3 is s.SO3 and RBF_mb(para=[1.0, 0.1]).l == 0.1\nprint('alias ok')\n" % ROOT)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "alias ok" in res.stdout, res.stderr[-2000:]
+
+
+def test_two_stage_contraction_emulation(capsys):
+    """The register-level algebra of the default no-gradient K_ff kernel (stage-1 accumulators fed unchanged as stage-2 A fragments,
+    stage-2 B fragments read from the production slab layout, a column tile that straddles two groups) against the direct pair
+    sums: numpy emulation of the m8n8k4 lane layouts (profiles/experiments/two_stage_emulation.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("two_stage_emulation",
+                                                  os.path.join(ROOT, "profiles", "experiments", "two_stage_emulation.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()                                  # asserts the 3x3 blocks to 1e-12
+    assert "two-stage vs direct" in capsys.readouterr().out
+
+
+def test_lml_eval_workspace_size():
+    """Host-only entry point of the C ABI: workspace of gprb_lml_eval = (NE + block of rows) x N doubles, block = max(512, N / parts)."""
+    from gpr_calculator_b200 import _lib
+    lib = _lib.load()
+    assert lib.gprb_lml_eval_work(32980, 340, 1, 16) == (340 + 2062) * 32980
+    assert lib.gprb_lml_eval_work(172, 4, 1, 16) == (4 + 172) * 172          # one block: the whole matrix
+    assert lib.gprb_lml_eval_work(32980, 340, 0, 16) == 0                    # no gradient: nothing to hold
